@@ -1,0 +1,125 @@
+/*
+ * nbp_b200.h -- C ABI of libnbp_b200.so: the B200-native exploration inner loop of NextBestPath.
+ *
+ * The reference (shiyao-li/NextBestPath) is pure Python and has no FFI; the interface each entry
+ * point replaces is a Python call site, cited below relative to /root/reference.  INTEGRATION.md
+ * shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all memory,
+ *     including workspaces (sizes from the *_workspace_bytes queries); the library never allocates,
+ *     frees or synchronises;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it;
+ *   - return value: 0 = OK, NBP_ERR_INVALID (<0) = bad argument, >0 = cudaError_t; a human-readable
+ *     message for the calling thread is available from nbp_last_error();
+ *   - ragged batches use CSR offsets; cameras are packed R[n,9] (row-major, world->view is
+ *     x_view = x_world * R + T with row vectors, PyTorch3D convention) and T[n,3];
+ *   - kernels are compiled for sm_100a only; there is no CPU fallback.
+ */
+#ifndef NBP_B200_H_
+#define NBP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBP_OK 0
+#define NBP_ERR_INVALID (-1)
+#define NBP_ERR_WORKSPACE (-2)
+#define NBP_ERR_UNSUPPORTED (-3)
+
+#define NBP_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------------------------ misc */
+int nbp_version(void);
+const char* nbp_last_error(void);
+/* number of kernel launches this library has enqueued from the calling process (bench gpu_launches) */
+uint64_t nbp_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------ a2
+ * Batched depth rasterisation.  Replaces Camera.capture_image's
+ *     images, fragments = self.renderer(mesh, cameras=fov_camera); depth = fragments.zbuf
+ * (macarons/utility/macarons_utils.py:2759-2762; renderer built at :905-937 with blur_radius 0,
+ * faces_per_pixel 1, FoVPerspectiveCameras fov 60 / znear 1 / z_clip znear/2).
+ *
+ * n_views cameras, view v looks at scene view_scene[v].  verts [sumV,3] fp32 packed;
+ * faces [sumF,3] int32 packed, indices LOCAL to the scene's vertex block.
+ * zbuf [n_views,H,W] fp32 view-space z, -1 where no face; pix_to_face [n_views,H,W] int32 scene-local
+ * face index or -1 (may be NULL).  total_view_faces = sum over views of the face count of its scene.
+ */
+size_t nbp_raster_workspace_bytes(int n_views, int64_t total_view_faces);
+int nbp_raster_depth_batched(const float* verts, const int32_t* faces,
+                             const int64_t* vert_offsets, const int64_t* face_offsets, int n_scenes,
+                             const int32_t* view_scene, const float* R, const float* T, int n_views,
+                             int64_t total_view_faces, int max_faces_per_scene,
+                             int H, int W, float tan_half_fov, float z_clip,
+                             float* zbuf, int32_t* pix_to_face,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------ a4+a5
+ * Depth back-projection, validity filter, subsample and append to per-scene point clouds.  Replaces
+ * Camera.compute_partial_point_cloud -> Camera.project_depth_in_3D -> unproject_points
+ * (macarons_utils.py:2811-2847, :2788-2809, NDC tables :2270-2279) and the growing
+ * torch.vstack((full_pc, part_pc)) at next_best_path/testers/nbp_planning.py:105,352.
+ *
+ * Frame f (zbuf[f], R[f], T[f]) belongs to cloud frame_scene[f].  A pixel is valid when
+ * zbuf > -1 (and mask != 0 when mask is given) and zbuf < fov_range (fov_range <= 0: no range test).
+ * Of the n valid pixels of a frame, k = (int)(n * gathering_factor) are kept:
+ *   gathering_factor >= 1 : all of them, in row-major pixel order (the parity path: the caller applies
+ *                           torch.randperm(n)[:k] itself, exactly as macarons_utils.py:2837);
+ *   otherwise             : the k pixels with the smallest keys of a keyed bijection of the pixel
+ *                           index (counter-based, seed + frame_uid[f]) -- a uniform random k-subset,
+ *                           written in row-major order.  Same distribution as randperm(n)[:k] as a SET;
+ *                           the consumer (the grid histogram) is order-independent.
+ * Points are appended to cloud[scene] (layout [n_scenes, cloud_capacity, 3] fp32) at cloud_len[scene],
+ * frames of one scene in frame order; cloud_len is updated.  Points beyond cloud_capacity are dropped
+ * and counted in *overflow (device int32, may be NULL).
+ * frame_valid / frame_kept [n_frames] int32 receive n and k (may be NULL).
+ */
+size_t nbp_backproject_workspace_bytes(int n_frames);
+int nbp_backproject_append(const float* zbuf, const uint8_t* mask, const float* R, const float* T,
+                           const int32_t* frame_scene, const int32_t* frame_uid, int n_frames,
+                           int H, int W, float tan_half_fov, float fov_range,
+                           double gathering_factor, uint64_t seed,
+                           float* cloud, int32_t* cloud_len, int64_t cloud_capacity, int n_scenes,
+                           int32_t* frame_valid, int32_t* frame_kept, int32_t* overflow,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------ a6-a10
+ * Height-slab split + egocentric transform + histogram into the model-input grid.  Replaces, per scene,
+ *     bins = torch.bucketize(full_pc[:, 1], y_bins[:-1]) - 1                (nbp_planning.py:114-115)
+ *     transform_points_to_n_pieces(..., no_rotation=True)                    (next_best_path/utility/utils.py:166-196)
+ *     map_points_to_n_imgs(points_2d, (S,S), (lo,hi), device)                (utils.py:198-223)
+ *     the trajectory image from camera.X_cam_history                         (nbp_planning.py:130-132)
+ *     torch.cat -> (1, n_pieces+1, S, S)                                     (nbp_planning.py:126-127,166)
+ *
+ * cloud [n_scenes, cloud_capacity, 3], cloud_len [n_scenes]; traj [n_scenes, traj_capacity, 3],
+ * traj_len [n_scenes] (traj may be NULL: channel n_pieces stays zero); pose [n_scenes,5] (x,y,z,elev,azim);
+ * slab_bounds [n_scenes, max_bounds] = the reference's y_bins[:-1] computed by the caller with the
+ * reference's own torch.arange expression (it has n_pieces or n_pieces+1 entries),
+ * n_bounds [n_scenes].  grid [n_scenes, n_pieces+1, S, S] fp32 counts; it is zeroed by this call.
+ * Cell indices are rint((p - lo) * fp32(S/(hi-lo))) with every operation rounded to fp32: bit-exact
+ * with torch.  max_points bounds the longest cloud (<= cloud_capacity) and only sizes the launch.
+ */
+int nbp_grid_scatter(const float* cloud, const int32_t* cloud_len, int64_t cloud_capacity,
+                     const float* traj, const int32_t* traj_len, int64_t traj_capacity,
+                     const float* pose, const float* slab_bounds, const int32_t* n_bounds, int max_bounds,
+                     int n_scenes, int n_pieces, int S, float range_lo, float range_hi,
+                     int64_t max_points, float* grid, void* stream);
+
+/* Plain map_points_to_n_imgs (utils.py:198-223): points_2d [n, m, 2] fp32 -> out [n, S0, S1] fp32
+ * counts (zeroed here).  n_valid_host: m may be ragged through lens [n] (NULL: all m). */
+int nbp_map_points(const float* points_2d, const int32_t* lens, int n, int64_t m, int S0, int S1,
+                   float range_lo, float range_hi, float* out, void* stream);
+
+/* get_point_position_in_the_img (utils.py:160-164): points [n,2] fp32 -> cells [2,n] int64. */
+int nbp_point_cells(const float* points_2d, int64_t n, int S0, int S1, float range_lo, float range_hi,
+                    int64_t* cells, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBP_B200_H_ */

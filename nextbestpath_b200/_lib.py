@@ -1,0 +1,58 @@
+"""ctypes binding of libnbp_b200.so (the C ABI declared in include/nbp_b200.h).
+
+There is no fallback: if the shared library is missing or does not load, importing any operator
+raises.  Build it with ``python -c "import __graft_entry__ as g; g.build()"``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnbp_b200.so")
+
+_p = C.c_void_p
+_i = C.c_int
+_l = C.c_int64
+_f = C.c_float
+_z = C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/nbp_b200.h one to one
+SIGNATURES = {
+    "nbp_version": (_i, []),
+    "nbp_last_error": (C.c_char_p, []),
+    "nbp_launch_count": (C.c_uint64, []),
+    "nbp_raster_workspace_bytes": (_z, [_i, _l]),
+    "nbp_raster_depth_batched": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _i, _l, _i, _i, _i, _f, _f, _p, _p, _p, _z, _p]),
+    "nbp_backproject_workspace_bytes": (_z, [_i]),
+    "nbp_backproject_append": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, C.c_double, C.c_uint64,
+                                    _p, _p, _l, _i, _p, _p, _p, _p, _z, _p]),
+    "nbp_grid_scatter": (_i, [_p, _p, _l, _p, _p, _l, _p, _p, _p, _i, _i, _i, _i, _f, _f, _l, _p, _p]),
+    "nbp_map_points": (_i, [_p, _p, _i, _l, _i, _i, _f, _f, _p, _p]),
+    "nbp_point_cells": (_i, [_p, _l, _i, _i, _f, _f, _p, _p]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises RuntimeError with build instructions if it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA extension is not built. "
+                "Run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). There is no CPU fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().nbp_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,253 @@
+// Depth back-projection + validity filter + k-subset selection + append to per-scene clouds
+// (SURVEY.md section 8 rows a4, a5).  Replaces Camera.compute_partial_point_cloud /
+// Camera.project_depth_in_3D (/root/reference/macarons/utility/macarons_utils.py:2788-2847) and the
+// growing torch.vstack at next_best_path/testers/nbp_planning.py:105,352.
+//
+// Three launches per call, one CTA (1024 threads) per frame in the two heavy ones:
+//   bp_select : count the n valid pixels; if k = int(n*gf) < n, radix-select (9-bit digits, shared
+//               histogram) the k-th smallest key of a keyed Feistel bijection of the pixel index.
+//   bp_offsets: per-frame append offsets (frames of one scene append in frame order) + new cloud_len.
+//   bp_write  : ordered compaction of the selected pixels, closed-form un-projection
+//               (oracle/oracle.py::unproject is the pin: one fp32 rounding per op), float stores.
+// zbuf is read 4x but only the first read comes from HBM (467 KB per frame stays in the 126 MB L2).
+#include "nbp_common.cuh"
+
+namespace nbp {
+
+static constexpr int BP_THREADS = 1024;
+
+struct FrameSel { int32_t n, k; uint32_t tau; int32_t base; int32_t final_len; int32_t pad[3]; };
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+
+// keyed bijection of [0, 2^(2*half)) : 6-round balanced Feistel network
+struct Feistel {
+    uint32_t rk[6]; int half; uint32_t hmask;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
+        uint32_t L = i >> half, R = i & hmask;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const uint32_t F = mix32(R * 0x9E3779B1U + rk[r]) & hmask;
+            const uint32_t nL = R;
+            R = L ^ F;
+            L = nL;
+        }
+        return (L << half) | R;
+    }
+};
+
+__device__ __forceinline__ Feistel make_feistel(uint64_t seed, int32_t uid, int key_bits) {
+    Feistel f;
+    f.half = key_bits / 2;
+    f.hmask = (1u << f.half) - 1u;
+    const uint32_t s0 = (uint32_t)seed, s1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) f.rk[r] = mix32(mix32(mix32(s0 + 0x632be5abU * (uint32_t)(r + 1)) ^ s1) ^ (uint32_t)uid);
+    return f;
+}
+
+struct BpParams {
+    const float* zbuf; const uint8_t* mask; const float* R; const float* T;
+    const int32_t* frame_scene; const int32_t* frame_uid; int n_frames;
+    int H, W, HW; float wm, hm, mm1; float tan_half, fov_range; double gf; uint64_t seed; int key_bits;
+    float* cloud; int32_t* cloud_len; int64_t cap; int n_scenes;
+    int32_t* frame_valid; int32_t* frame_kept; int32_t* overflow;
+    FrameSel* sel;
+};
+
+__device__ __forceinline__ bool pixel_valid(const BpParams& p, const float* z, const uint8_t* m, int i) {
+    const float d = __ldg(z + i);
+    bool v = d > -1.0f;
+    if (m) v = v && (m[i] != 0);
+    if (p.fov_range > 0.0f) v = v && (d < p.fov_range);
+    return v;
+}
+
+__global__ void __launch_bounds__(BP_THREADS) bp_select(BpParams p) {
+    __shared__ int s_hist[512];
+    __shared__ int s_red[BP_THREADS / 32];
+    __shared__ uint32_t s_prefix; __shared__ int s_krem; __shared__ int s_n;
+
+    const int f = blockIdx.x;
+    const float* z = p.zbuf + (size_t)f * p.HW;
+    const uint8_t* m = p.mask ? p.mask + (size_t)f * p.HW : nullptr;
+
+    // ---- count valid
+    int cnt = 0;
+    for (int i = threadIdx.x; i < p.HW; i += BP_THREADS) cnt += pixel_valid(p, z, m, i) ? 1 : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    if (lane_id() == 0) s_red[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int w = 0; w < BP_THREADS / 32; ++w) n += s_red[w];
+        s_n = n;
+    }
+    __syncthreads();
+    const int n = s_n;
+    int k = (p.gf >= 1.0) ? n : (int)((double)n * p.gf);
+    if (k > n) k = n;
+    if (k < 0) k = 0;
+
+    uint32_t tau = 0xffffffffu;
+    if (k > 0 && k < n) {
+        const Feistel perm = make_feistel(p.seed, p.frame_uid ? p.frame_uid[f] : f, p.key_bits);
+        if (threadIdx.x == 0) { s_prefix = 0; s_krem = k; }
+        int bits_left = p.key_bits;
+        while (bits_left > 0) {
+            const int db = bits_left >= 9 ? 9 : bits_left;       // digit width of this pass
+            const int shift = bits_left - db;
+            for (int b = threadIdx.x; b < 512; b += BP_THREADS) s_hist[b] = 0;
+            __syncthreads();
+            const uint32_t prefix = s_prefix;                    // already-fixed high bits (aligned at `bits_left`)
+            for (int i = threadIdx.x; i < p.HW; i += BP_THREADS) {
+                if (!pixel_valid(p, z, m, i)) continue;
+                const uint32_t key = perm((uint32_t)i);
+                if ((key >> bits_left) != prefix) continue;
+                atomicAdd(&s_hist[(key >> shift) & ((1u << db) - 1u)], 1);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int krem = s_krem, acc = 0, d = 0;
+                const int nb = 1 << db;
+                for (; d < nb; ++d) {
+                    if (acc + s_hist[d] >= krem) break;
+                    acc += s_hist[d];
+                }
+                if (d >= nb) d = nb - 1;                          // cannot happen (k <= n)
+                s_krem = krem - acc;
+                s_prefix = (prefix << db) | (uint32_t)d;
+            }
+            __syncthreads();
+            bits_left = shift;
+        }
+        tau = s_prefix;     // keys are unique: exactly k valid pixels have key <= tau
+    }
+    if (threadIdx.x == 0) {
+        FrameSel s; s.n = n; s.k = k; s.tau = tau; s.base = 0; s.final_len = -1; s.pad[0] = s.pad[1] = s.pad[2] = 0;
+        p.sel[f] = s;
+        if (p.frame_valid) p.frame_valid[f] = n;
+        if (p.frame_kept) p.frame_kept[f] = k;
+    }
+}
+
+__global__ void bp_offsets(BpParams p) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < p.n_frames; f += gridDim.x * blockDim.x) {
+        const int s = p.frame_scene[f];
+        int base = p.cloud_len[s];
+        bool last = true;
+        for (int g = 0; g < p.n_frames; ++g) {
+            if (p.frame_scene[g] != s) continue;
+            if (g < f) base += p.sel[g].k;
+            if (g > f) last = false;
+        }
+        p.sel[f].base = base;
+        if (last) {
+            int64_t e = (int64_t)base + p.sel[f].k;
+            p.sel[f].final_len = (int32_t)(e > p.cap ? p.cap : e);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BP_THREADS) bp_write(BpParams p) {
+    __shared__ int s_wcnt[BP_THREADS / 32];
+    __shared__ float sR[9], sT[3];
+    const int f = blockIdx.x;
+    const FrameSel sel = p.sel[f];
+    const int scene = p.frame_scene[f];
+    if (threadIdx.x < 9) sR[threadIdx.x] = p.R[f * 9 + threadIdx.x];
+    if (threadIdx.x < 3) sT[threadIdx.x] = p.T[f * 3 + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0 && sel.final_len >= 0) p.cloud_len[scene] = sel.final_len;   // bp_offsets already read the old value
+    if (sel.k == 0) return;
+
+    const float* z = p.zbuf + (size_t)f * p.HW;
+    const uint8_t* m = p.mask ? p.mask + (size_t)f * p.HW : nullptr;
+    const bool all = sel.k == sel.n;
+    const Feistel perm = make_feistel(p.seed, p.frame_uid ? p.frame_uid[f] : f, p.key_bits);
+    float* out = p.cloud + (size_t)scene * (size_t)p.cap * 3;
+
+    const float wm = p.wm, hm = p.hm, mm1 = p.mm1;
+    int running = sel.base, dropped = 0;
+    for (int c0 = 0; c0 < p.HW; c0 += BP_THREADS) {
+        const int i = c0 + threadIdx.x;
+        bool keep = false;
+        if (i < p.HW && pixel_valid(p, z, m, i)) keep = all || perm((uint32_t)i) <= sel.tau;
+        int tot;
+        const int slot = running + block_compact(keep, s_wcnt, tot);
+        running += tot;
+        if (keep) {
+            if (slot < p.cap) {
+                const int row = i / p.W, col = i - row * p.W;
+                const float d = z[i];
+                // NDC tables of macarons_utils.py:2270-2279
+                const float nx = fsub(wm, fmul(fdiv((float)col, mm1), 2.0f));
+                const float ny = fsub(hm, fmul(fdiv((float)row, mm1), 2.0f));
+                const float s = fmul(d, p.tan_half);
+                const float dx = fsub(fmul(nx, s), sT[0]);
+                const float dy = fsub(fmul(ny, s), sT[1]);
+                const float dz = fsub(d, sT[2]);
+                float* o = out + (size_t)slot * 3;
+                o[0] = fadd(fadd(fmul(dx, sR[0]), fmul(dy, sR[1])), fmul(dz, sR[2]));
+                o[1] = fadd(fadd(fmul(dx, sR[3]), fmul(dy, sR[4])), fmul(dz, sR[5]));
+                o[2] = fadd(fadd(fmul(dx, sR[6]), fmul(dy, sR[7])), fmul(dz, sR[8]));
+            } else {
+                ++dropped;
+            }
+        }
+    }
+    if (dropped && p.overflow) atomicAdd(p.overflow, dropped);
+}
+
+}  // namespace nbp
+
+using namespace nbp;
+
+extern "C" size_t nbp_backproject_workspace_bytes(int n_frames) {
+    if (n_frames < 0) return 0;
+    return sizeof(FrameSel) * (size_t)(n_frames + 1);
+}
+
+extern "C" int nbp_backproject_append(const float* zbuf, const uint8_t* mask, const float* R, const float* T,
+                                      const int32_t* frame_scene, const int32_t* frame_uid, int n_frames,
+                                      int H, int W, float tan_half_fov, float fov_range,
+                                      double gathering_factor, uint64_t seed,
+                                      float* cloud, int32_t* cloud_len, int64_t cloud_capacity, int n_scenes,
+                                      int32_t* frame_valid, int32_t* frame_kept, int32_t* overflow,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+    if (n_frames == 0) return NBP_OK;
+    if (!zbuf || !R || !T || !frame_scene || !cloud || !cloud_len)
+        return invalid("nbp_backproject_append: null pointer argument");
+    if (n_frames < 0 || H <= 0 || W <= 0 || n_scenes <= 0 || cloud_capacity <= 0 || (int64_t)H * W > (1 << 26))
+        return invalid("nbp_backproject_append: bad sizes n_frames=%d H=%d W=%d n_scenes=%d cap=%lld", n_frames, H, W,
+                       n_scenes, (long long)cloud_capacity);
+    if (cloud_capacity > 0x7fffffffLL) return invalid("nbp_backproject_append: cloud_capacity must fit int32");
+    if (!(tan_half_fov > 0.0f)) return invalid("nbp_backproject_append: tan_half_fov must be positive");
+    if (!(gathering_factor >= 0.0)) return invalid("nbp_backproject_append: gathering_factor must be >= 0");
+    const size_t need = nbp_backproject_workspace_bytes(n_frames);
+    if (!workspace || workspace_bytes < need) {
+        set_error("nbp_backproject_append: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return NBP_ERR_WORKSPACE;
+    }
+    int key_bits = 2;
+    while ((1LL << key_bits) < (int64_t)H * W) key_bits += 2;     // even, so the Feistel halves balance
+    // python: W / min(W, H) is a double, cast to fp32 when combined with the fp32 table (macarons_utils.py:2272-2277)
+    const int mn = H < W ? H : W;
+    const float wm = (float)((double)W / (double)mn), hm = (float)((double)H / (double)mn), mm1 = (float)(mn - 1);
+    if (mn < 2) return invalid("nbp_backproject_append: H and W must be >= 2");
+    BpParams p{zbuf, mask, R, T, frame_scene, frame_uid, n_frames, H, W, H * W, wm, hm, mm1, tan_half_fov, fov_range,
+               gathering_factor, seed, key_bits, cloud, cloud_len, cloud_capacity, n_scenes,
+               frame_valid, frame_kept, overflow, (FrameSel*)workspace};
+    cudaStream_t st = (cudaStream_t)stream;
+    bp_select<<<n_frames, BP_THREADS, 0, st>>>(p);
+    count_launch();
+    bp_offsets<<<(n_frames + 255) / 256, 256, 0, st>>>(p);
+    count_launch();
+    bp_write<<<n_frames, BP_THREADS, 0, st>>>(p);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "nbp_backproject_append launch");
+}
