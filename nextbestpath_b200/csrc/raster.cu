@@ -284,8 +284,10 @@ extern "C" int nbp_raster_depth_batched(const float* verts, const int32_t* faces
                                         float* zbuf, int32_t* pix_to_face,
                                         void* workspace, size_t workspace_bytes, void* stream) {
     if (n_views == 0) return NBP_OK;
-    if (!verts || !faces || !vert_offsets || !face_offsets || !view_scene || !R || !T || !zbuf)
+    if (!vert_offsets || !face_offsets || !view_scene || !R || !T || !zbuf)
         return invalid("nbp_raster_depth_batched: null pointer argument");
+    if (max_faces_per_scene > 0 && (!verts || !faces))
+        return invalid("nbp_raster_depth_batched: null verts/faces with a non-empty mesh");
     if (n_views < 0 || n_scenes <= 0 || H <= 0 || W <= 0 || H > 32767 || W > 32767)
         return invalid("nbp_raster_depth_batched: bad sizes n_views=%d n_scenes=%d H=%d W=%d", n_views, n_scenes, H, W);
     if (n_views > 65535) return invalid("nbp_raster_depth_batched: n_views=%d exceeds 65535 per call", n_views);
