@@ -16,6 +16,8 @@ SOURCES = {
     "raster.cu": ["-fmad=false"],
     "backproject.cu": ["-fmad=false"],
     "scatter.cu": ["-fmad=false"],
+    "conv_tc.cu": [],
+    "nn_kernels.cu": [],
 }
 
 

@@ -1,0 +1,338 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05 + TMEM + TMA) for the NBP
+// attention-U-Net (/root/reference/next_best_path/networks/nbp_model.py:8-62,110-160).
+//
+//   out[n,y,x,co] = act( scale[co] * sum_{tap,ci} in[n, y+dy, x+dx, ci] * w[co, tap, ci] + shift[co] )
+//
+// Layout: activations NHWC fp16 (channel counts multiples of 64), weights fp16 [c_out][taps][c_in] (K-major),
+// accumulation fp32 in TMEM, epilogue affine (folded conv bias + BatchNorm) in fp32, output NHWC fp16.
+// fp16 storage was chosen over tf32/bf16 from a measured error budget: 2.0e-4 relative on out1
+// vs 1.75e-3 for bf16, at twice the tensor rate of tf32.
+//
+// GEMM view per CTA tile: M = 128 output pixels (a tw x th x tn box of the image batch), N = BLOCK_N output
+// channels, K = taps * c_in walked in 64-channel slices.  No im2col buffer exists anywhere: the A operand of
+// tap (dy,dx) is the SAME 4-D TMA box shifted by (dx,dy); TMA zero-fills the out-of-image halo, which is the
+// conv's zero padding.  Channel concatenation (torch.cat((skip*psi, up), 1), nbp_model.py:128) is fused by
+// walking two source tensors inside the K loop.
+//
+// Warp roles (256 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0 : TMA producer (one elected lane)      smem ring of STAGES x {A 16 KB, B BLOCK_N*128 B}
+//   warp 1 : tcgen05.mma issuer (one elected lane) 4 x (128 x BLOCK_N x 16) UMMAs per stage
+//   warp 2 : TMEM allocator
+//   warps 4-7 : epilogue, TMEM -> registers -> affine/ReLU -> fp16 -> global; double-buffered accumulators
+//               so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+
+#include "nbp_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace nbp {
+
+using namespace tc;
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;                         // fp16 elements = one 128-byte swizzle row
+static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+static constexpr int CONV_THREADS = 256;
+static constexpr int SMEM_LIMIT = 232448;                  // 227 KB opt-in maximum per CTA
+static constexpr int SMEM_AUX = 4096;                      // barriers + tmem ptr + scale/shift staging
+
+struct ConvKParams {
+    int n, h, w;
+    int tw, th, tn, tiles_x, tiles_y, tiles_n;
+    int m_tiles, n_tiles;
+    int taps, kc0, kc1;
+    const float* scale; const float* shift;
+    int relu;
+    __half* dst; int dst_ld, dst_c_off;
+};
+
+template <int BLOCK_N>
+struct ConvCfg {
+    static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES_RAW = (SMEM_LIMIT - SMEM_AUX - 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_AUX + 1024;   // +1024: manual 1024-B alignment
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+              const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
+    using Cfg = ConvCfg<BLOCK_N>;
+    constexpr int STAGES = Cfg::STAGES;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+    uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);              // [STAGES]
+    uint64_t* empty_bar = full_bar + STAGES;                            // [STAGES]
+    uint64_t* tfull_bar = empty_bar + STAGES;                           // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                               // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* s_affine = reinterpret_cast<float*>(aux + 512);              // [2 acc][2][BLOCK_N]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA0); prefetch_tmap(&tmA1); prefetch_tmap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int num_tiles = p.m_tiles * p.n_tiles;
+    const int kc_total = p.kc0 + p.kc1;
+    const int num_k = p.taps * kc_total;
+
+    if (warp == 0) {
+        // ================================================================= TMA producer
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.n_tiles;
+                int mt = tile / p.n_tiles;
+                const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+                const int ty = mt % p.tiles_y;
+                const int tb = mt / p.tiles_y;
+                const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tb * p.tn;
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
+                    const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+                    for (int kc = 0; kc < kc_total; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                        if (kc < p.kc0) tma_load_4d(smem_a + stage * A_STAGE_BYTES, &tmA0, &full_bar[stage], kc * BLOCK_K, x0 + dx, y0 + dy, n0);
+                        else            tma_load_4d(smem_a + stage * A_STAGE_BYTES, &tmA1, &full_bar[stage], (kc - p.kc0) * BLOCK_K, x0 + dx, y0 + dy, n0);
+                        tma_load_2d(smem_b + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], (tap * kc_total + kc) * BLOCK_K, n_tile * BLOCK_N);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_f16(BLOCK_M, BLOCK_N);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int ks = 0; ks < num_k; ++ks) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
+                    const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k) {
+                        // +32 bytes (16 fp16) along K inside the 128-byte swizzle row: +2 in the encoded address
+                        umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);           // frees the smem slot once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);                  // accumulator complete -> epilogue
+                acc ^= 1; if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================================================= epilogue (4 warps = 128 TMEM lanes)
+        const int q = warp & 3;                                 // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;                            // accumulator row = pixel of the tile
+        const int et = threadIdx.x - 128;                       // 0..127
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int n_tile = tile % p.n_tiles;
+            int mt = tile / p.n_tiles;
+            const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+            const int ty = mt % p.tiles_y;
+            const int tb = mt / p.tiles_y;
+            const int wi = m % p.tw, hi = (m / p.tw) % p.th, ni = m / (p.tw * p.th);
+            const int x = tx * p.tw + wi, y = ty * p.th + hi, nn = tb * p.tn + ni;
+            const bool valid = x < p.w && y < p.h && nn < p.n;
+
+            // stage this tile's affine into smem (buffer `acc`: the previous user of this buffer finished
+            // two tiles ago, and the named barrier below orders the writes before the reads)
+            float* sa = s_affine + acc * 2 * BLOCK_N;
+            for (int i = et; i < BLOCK_N; i += 128) {
+                sa[i] = p.scale[n_tile * BLOCK_N + i];
+                sa[BLOCK_N + i] = p.shift[n_tile * BLOCK_N + i];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            __half* orow = p.dst + ((size_t)((size_t)nn * p.h + y) * p.w + x) * p.dst_ld + p.dst_c_off + n_tile * BLOCK_N;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
+                tmem_ld_wait();
+                uint32_t packed[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int col = c * 32 + 2 * j;
+                    float a0 = fmaf(__uint_as_float(v[2 * j]), sa[col], sa[BLOCK_N + col]);
+                    float a1 = fmaf(__uint_as_float(v[2 * j + 1]), sa[col + 1], sa[BLOCK_N + col + 1]);
+                    if (p.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); }
+                    a0 = fminf(fmaxf(a0, -65504.0f), 65504.0f);
+                    a1 = fminf(fmaxf(a1, -65504.0f), 65504.0f);
+                    const __half2 h = __floats2half2_rn(a0, a1);
+                    packed[j] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                if (valid) {
+                    uint4* o = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// NHWC fp16 activation [n][h][w][ld] (first `c` channels used) -> 4-D map (c, w, h, n), box (64, tw, th, tn), 128B swizzle
+static int make_act_map(CUtensorMap* m, const void* ptr, int c, int ld, int n, int h, int w, int tw, int th, int tn) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return NBP_ERR_UNSUPPORTED; }
+    cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)w * ld * 2, (cuuint64_t)h * w * ld * 2};
+    cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation c=%d ld=%d n=%d h=%d w=%d box=%d,%d,%d) failed: %d", c, ld, n, h, w, tw, th, tn, (int)r); return NBP_ERR_INVALID; }
+    return NBP_OK;
+}
+
+static int make_weight_map(CUtensorMap* m, const void* ptr, int k_total, int c_out, int block_n) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return NBP_ERR_UNSUPPORTED; }
+    cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)c_out};
+    cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+    cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)block_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weight k=%d c_out=%d) failed: %d", k_total, c_out, (int)r); return NBP_ERR_INVALID; }
+    return NBP_OK;
+}
+
+static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+static int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
+
+template <int BLOCK_N>
+static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvKParams& kp, int sms, cudaStream_t st) {
+    using Cfg = ConvCfg<BLOCK_N>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        int rc = check_cuda(cudaFuncSetAttribute(conv_gemm_f16<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES),
+                            "cudaFuncSetAttribute(conv_gemm_f16)");
+        if (rc) return rc;
+        attr_set = true;
+    }
+    const int tiles = kp.m_tiles * kp.n_tiles;
+    const int grid = tiles < sms ? tiles : sms;
+    conv_gemm_f16<BLOCK_N><<<grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b, kp);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "conv_gemm_f16 launch");
+}
+
+}  // namespace nbp
+
+using namespace nbp;
+
+extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
+    if (!d) return invalid("nbp_conv_fwd: null descriptor");
+    if (!d->src0 || !d->weight || !d->scale || !d->shift || !d->dst) return invalid("nbp_conv_fwd: null pointer in descriptor");
+    if (d->taps != 1 && d->taps != 9) return invalid("nbp_conv_fwd: taps must be 1 or 9 (got %d)", d->taps);
+    if (d->n <= 0 || d->h <= 0 || d->w <= 0) return invalid("nbp_conv_fwd: bad image dims n=%d h=%d w=%d", d->n, d->h, d->w);
+    if (d->c0 <= 0 || d->c0 % BLOCK_K || d->c1 < 0 || d->c1 % BLOCK_K || (d->c1 > 0 && !d->src1))
+        return invalid("nbp_conv_fwd: source channels must be positive multiples of 64 (c0=%d c1=%d)", d->c0, d->c1);
+    if (d->ld0 < d->c0 || d->ld0 % 8 || (d->c1 > 0 && (d->ld1 < d->c1 || d->ld1 % 8)))
+        return invalid("nbp_conv_fwd: source channel strides must be >= channels and multiples of 8");
+    if (d->c_out <= 0 || d->c_out % 32) return invalid("nbp_conv_fwd: c_out must be a positive multiple of 32 (got %d)", d->c_out);
+    if (d->dst_ld % 8 || d->dst_c_off % 8 || d->dst_c_off + d->c_out > d->dst_ld)
+        return invalid("nbp_conv_fwd: bad destination channel layout ld=%d off=%d c_out=%d", d->dst_ld, d->dst_c_off, d->c_out);
+    if (((uintptr_t)d->src0 | (uintptr_t)d->src1 | (uintptr_t)d->weight | (uintptr_t)d->dst) & 15)
+        return invalid("nbp_conv_fwd: pointers must be 16-byte aligned");
+
+    const int block_n = (d->c_out % 128 == 0) ? 128 : (d->c_out % 64 == 0) ? 64 : 32;
+    ConvKParams kp{};
+    kp.n = d->n; kp.h = d->h; kp.w = d->w;
+    kp.tw = d->w >= 16 ? 16 : pow2_floor(d->w);
+    int th = BLOCK_M / kp.tw; const int hc = pow2_ceil(d->h);
+    kp.th = th < hc ? th : hc;
+    kp.tn = BLOCK_M / (kp.tw * kp.th);
+    kp.tiles_x = (d->w + kp.tw - 1) / kp.tw; kp.tiles_y = (d->h + kp.th - 1) / kp.th; kp.tiles_n = (d->n + kp.tn - 1) / kp.tn;
+    kp.m_tiles = kp.tiles_x * kp.tiles_y * kp.tiles_n; kp.n_tiles = d->c_out / block_n;
+    kp.taps = d->taps; kp.kc0 = d->c0 / BLOCK_K; kp.kc1 = d->c1 / BLOCK_K;
+    kp.scale = d->scale; kp.shift = d->shift; kp.relu = d->relu;
+    kp.dst = (__half*)d->dst; kp.dst_ld = d->dst_ld; kp.dst_c_off = d->dst_c_off;
+    if (kp.tn > 256 || kp.th > 256) return invalid("nbp_conv_fwd: image too small for a 128-pixel tile (w=%d h=%d)", d->w, d->h);
+
+    CUtensorMap a0, a1, b;
+    int rc = make_act_map(&a0, d->src0, d->c0, d->ld0, d->n, d->h, d->w, kp.tw, kp.th, kp.tn);
+    if (rc) return rc;
+    if (d->c1 > 0) rc = make_act_map(&a1, d->src1, d->c1, d->ld1, d->n, d->h, d->w, kp.tw, kp.th, kp.tn);
+    else a1 = a0;
+    if (rc) return rc;
+    rc = make_weight_map(&b, d->weight, d->taps * (d->c0 + d->c1), d->c_out, block_n);
+    if (rc) return rc;
+
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+        if (rc) return rc;
+        rc = check_cuda(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
+        if (rc) return rc;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (block_n) {
+        case 128: return launch_conv<128>(a0, a1, b, kp, sms, st);
+        case 64:  return launch_conv<64>(a0, a1, b, kp, sms, st);
+        default:  return launch_conv<32>(a0, a1, b, kp, sms, st);
+    }
+}
