@@ -126,33 +126,41 @@ int nbp_point_cells(const float* points_2d, int64_t n, int S0, int S1, float ran
  * offsets let a producer write straight into a concatenation buffer (torch.cat at :128,133,...).
  */
 typedef struct nbp_conv_desc {
-    const void* src0; int c0; int ld0;     /* NHWC fp16, first c0 channels of rows with stride ld0 */
-    const void* src1; int c1; int ld1;     /* optional second source, concatenated after src0 along channels */
+    int precise;                           /* 1: fp16x2 split format (hi plane + lo*2048 plane), fp32-grade results;
+                                              0: single fp16 plane */
+    const void* src0; int c0; int ld0; int lo0;  /* NHWC fp16: c0 channels per pixel, pixel stride ld0 elements; with
+                                              precise, the lo plane starts lo0 elements after src0 */
+    const void* src1; int c1; int ld1; int lo1;  /* optional second source, concatenated after src0 along channels */
     int n, h, w;                           /* images and spatial size (stride 1, same-size output) */
     int taps;                              /* 1 = 1x1 conv, 9 = 3x3 conv with zero padding 1 */
-    const void* weight;                    /* fp16 [c_out][taps][c0+c1] (K-major); tap = ky*3+kx */
+    const void* weight;                    /* fp16 [c_out][taps][c0+c1] (K-major); tap = ky*3+kx.  precise: per tile of
+                                              BN = 128|64|32 output channels (largest dividing c_out) BN hi rows then BN lo rows */
     int c_out;                             /* multiple of 32 */
     const float* scale; const float* shift;/* [c_out] fp32: y = acc*scale + shift */
     int relu;
     void* dst; int dst_ld; int dst_c_off;  /* NHWC fp16 output, written at channels [dst_c_off, dst_c_off+c_out) */
+    int dst_lo_off;                        /* precise: lo plane written dst_lo_off elements after the hi channels */
 } nbp_conv_desc;
 
 /* tcgen05/TMEM/TMA implicit-GEMM convolution: conv_block / up_conv / Attention_block W_g,W_x (nbp_model.py:8-62) */
 int nbp_conv_fwd(const nbp_conv_desc* desc, void* stream);
-/* Conv1.conv.0: x fp32 NCHW [n,c_in,h,w] counts -> NHWC fp16 [n,h,w,dst_ld]; weight fp32 [9*c_in][c_out]
+/* The pointwise kernels below take, for every NHWC fp16 tensor, the pixel stride `ld` (elements) and the
+ * offset `lo` of the lo plane of the fp16x2 format (0 = single-plane fp16 tensor). */
+/* Conv1.conv.0: x fp32 NCHW [n,c_in,h,w] counts -> NHWC fp16; weight fp32 [9*c_in][c_out]
  * (tap-major, then input channel), c_out = 64; fused affine + ReLU (nbp_model.py:11-13) */
 int nbp_conv_first(const float* x, int n, int c_in, int h, int w, const float* weight, const float* scale,
-                   const float* shift, int c_out, void* dst, int dst_ld, void* stream);
+                   const float* shift, int c_out, void* dst, int dst_ld, int dst_lo, void* stream);
 /* nn.MaxPool2d(2,2) (nbp_model.py:68) and nn.Upsample(scale_factor=2) nearest (:27) on NHWC fp16 */
-int nbp_maxpool2x2(const void* src, int n, int h, int w, int c, int ld_src, void* dst, int ld_dst, void* stream);
-int nbp_upsample2x(const void* src, int n, int h, int w, int c, int ld_src, void* dst, int ld_dst, void* stream);
+int nbp_maxpool2x2(const void* src, int n, int h, int w, int c, int ld_src, int lo_src, void* dst, int ld_dst, int lo_dst, void* stream);
+int nbp_upsample2x(const void* src, int n, int h, int w, int c, int ld_src, int lo_src, void* dst, int ld_dst, int lo_dst, void* stream);
 /* Attention_block tail (nbp_model.py:49-62): psi = sigmoid(psi_scale * dot(a, w_psi) + psi_shift); dst = x * psi.
- * a [npix][f_int] fp16 = relu(BN(W_g g) + BN(W_x x)); x [npix][ld_x]; dst [npix][dst_ld] at channel dst_c_off */
-int nbp_att_gate(const void* a, int f_int, const void* x, int f_l, int ld_x, const float* w_psi, float psi_scale,
-                 float psi_shift, void* dst, int dst_ld, int dst_c_off, int64_t npix, void* stream);
+ * a [npix] x f_int = relu(BN(W_g g) + BN(W_x x)); x [npix] x f_l; dst written at channel dst_c_off */
+int nbp_att_gate(const void* a, int f_int, int ld_a, int lo_a, const void* x, int f_l, int ld_x, int lo_x,
+                 const float* w_psi, float psi_scale, float psi_shift,
+                 void* dst, int dst_ld, int dst_c_off, int dst_lo, int64_t npix, void* stream);
 /* Final1 (256->8) and Final2 (64->1, sigmoid) (nbp_model.py:89,106-108): NHWC fp16 in, NCHW fp32 out [n,c_out,hw];
  * weight fp32 [c_out][c_in], c_out in {1, 8} */
-int nbp_conv1x1_head(const void* src, int c_in, int ld_src, const float* weight, const float* bias, int c_out,
+int nbp_conv1x1_head(const void* src, int c_in, int ld_src, int lo_src, const float* weight, const float* bias, int c_out,
                      int sigmoid, float* dst, int n, int64_t hw, void* stream);
 
 #ifdef __cplusplus

@@ -36,18 +36,20 @@ SIGNATURES = {
 
 class ConvDesc(C.Structure):
     """struct nbp_conv_desc (include/nbp_b200.h)."""
-    _fields_ = [("src0", _p), ("c0", _i), ("ld0", _i), ("src1", _p), ("c1", _i), ("ld1", _i),
+    _fields_ = [("precise", _i), ("src0", _p), ("c0", _i), ("ld0", _i), ("lo0", _i),
+                ("src1", _p), ("c1", _i), ("ld1", _i), ("lo1", _i),
                 ("n", _i), ("h", _i), ("w", _i), ("taps", _i), ("weight", _p), ("c_out", _i),
-                ("scale", _p), ("shift", _p), ("relu", _i), ("dst", _p), ("dst_ld", _i), ("dst_c_off", _i)]
+                ("scale", _p), ("shift", _p), ("relu", _i), ("dst", _p), ("dst_ld", _i), ("dst_c_off", _i),
+                ("dst_lo_off", _i)]
 
 
 SIGNATURES.update({
     "nbp_conv_fwd": (_i, [C.POINTER(ConvDesc), _p]),
-    "nbp_conv_first": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p]),
-    "nbp_maxpool2x2": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p]),
-    "nbp_upsample2x": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p]),
-    "nbp_att_gate": (_i, [_p, _i, _p, _i, _i, _p, _f, _f, _p, _i, _i, _l, _p]),
-    "nbp_conv1x1_head": (_i, [_p, _i, _i, _p, _p, _i, _i, _p, _i, _l, _p]),
+    "nbp_conv_first": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _i, _p]),
+    "nbp_maxpool2x2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
+    "nbp_upsample2x": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
+    "nbp_att_gate": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p, _f, _f, _p, _i, _i, _i, _l, _p]),
+    "nbp_conv1x1_head": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _i, _l, _p]),
 })
 
 _lib = None

@@ -12,12 +12,48 @@
 
 namespace nbp {
 
+// Activation format helpers.  A tensor is NHWC fp16; in the fp16x2 ("precise") format each pixel carries a
+// second plane holding (value - hi) * 2048, `lo` elements after the first (lo == 0: single plane).
+static constexpr float LO_SCALE = 2048.0f;
+
+__device__ __forceinline__ void load8(const __half* p, int lo, float* f) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* hq = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 t = __half22float2(hq[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+    if (lo) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(p + lo));
+        const __half2* hr = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 t = __half22float2(hr[j]);
+            f[2 * j] = fmaf(t.x, 1.0f / LO_SCALE, f[2 * j]);
+            f[2 * j + 1] = fmaf(t.y, 1.0f / LO_SCALE, f[2 * j + 1]);
+        }
+    }
+}
+
+__device__ __forceinline__ void store8(__half* p, int lo, const float* f) {
+    uint32_t hi[4], lw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a0 = fminf(fmaxf(f[2 * j], -65504.0f), 65504.0f), a1 = fminf(fmaxf(f[2 * j + 1], -65504.0f), 65504.0f);
+        const __half2 h = __floats2half2_rn(a0, a1);
+        hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn((a0 - hf.x) * LO_SCALE, (a1 - hf.y) * LO_SCALE);
+        lw[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (lo) *reinterpret_cast<uint4*>(p + lo) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
 // ------------------------------------------------------------------------------------------------ conv_first
 template <int COUT>
 __global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict__ x, int n, int cin, int h, int w,
                                                          const float* __restrict__ wt,      // [9*cin][COUT]
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
-                                                         __half* __restrict__ dst, int dst_ld) {
+                                                         __half* __restrict__ dst, int dst_ld, int dst_lo) {
     extern __shared__ float s_w[];                    // 9*cin*COUT weights, then scale, shift
     const int nw = 9 * cin * COUT;
     for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = wt[i];
@@ -51,35 +87,20 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict
                 }
             }
         }
-        uint4* o = reinterpret_cast<uint4*>(dst + pix * dst_ld);
+        __half* o = dst + pix * dst_ld;
 #pragma unroll
         for (int c8 = 0; c8 < COUT / 8; ++c8) {
-            uint32_t pk[4];
+            float f[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = 8 * c8 + 2 * j;
-                float a0 = fmaxf(fmaf(acc[c], s_sc[c], s_sh[c]), 0.0f);
-                float a1 = fmaxf(fmaf(acc[c + 1], s_sc[c + 1], s_sh[c + 1]), 0.0f);
-                const __half2 hh = __floats2half2_rn(fminf(a0, 65504.0f), fminf(a1, 65504.0f));
-                pk[j] = *reinterpret_cast<const uint32_t*>(&hh);
-            }
-            o[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(acc[8 * c8 + j], s_sc[8 * c8 + j], s_sh[8 * c8 + j]), 0.0f);
+            store8(o + 8 * c8, dst_lo, f);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------ pool / upsample
-__device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
-    uint4 r;
-    const __half2* pa = reinterpret_cast<const __half2*>(&a); const __half2* pb = reinterpret_cast<const __half2*>(&b);
-    __half2* pr = reinterpret_cast<__half2*>(&r);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
-    return r;
-}
-
-__global__ void __launch_bounds__(256) maxpool2x2_kernel(const __half* __restrict__ src, int n, int h, int w, int c, int ld_src,
-                                                         __half* __restrict__ dst, int ld_dst) {
+__global__ void __launch_bounds__(256) maxpool2x2_kernel(const __half* __restrict__ src, int n, int h, int w, int c, int ld_src, int lo_src,
+                                                         __half* __restrict__ dst, int ld_dst, int lo_dst) {
     const int ho = h / 2, wo = w / 2, c8 = c / 8;
     const size_t total = (size_t)n * ho * wo * c8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -87,33 +108,37 @@ __global__ void __launch_bounds__(256) maxpool2x2_kernel(const __half* __restric
         const int xo = (int)(t % wo); t /= wo;
         const int yo = (int)(t % ho); const int img = (int)(t / ho);
         const __half* p = src + (((size_t)img * h + 2 * yo) * w + 2 * xo) * ld_src + 8 * cc;
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
-        const uint4 b = __ldg(reinterpret_cast<const uint4*>(p + ld_src));
-        const uint4 d = __ldg(reinterpret_cast<const uint4*>(p + (size_t)w * ld_src));
-        const uint4 e = __ldg(reinterpret_cast<const uint4*>(p + (size_t)w * ld_src + ld_src));
-        *reinterpret_cast<uint4*>(dst + (((size_t)img * ho + yo) * wo + xo) * ld_dst + 8 * cc) = hmax8(hmax8(a, b), hmax8(d, e));
+        float a[8], b[8], d[8], e[8];
+        load8(p, lo_src, a); load8(p + ld_src, lo_src, b);
+        load8(p + (size_t)w * ld_src, lo_src, d); load8(p + (size_t)w * ld_src + ld_src, lo_src, e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = fmaxf(fmaxf(a[j], b[j]), fmaxf(d[j], e[j]));
+        store8(dst + (((size_t)img * ho + yo) * wo + xo) * ld_dst + 8 * cc, lo_dst, a);     // hi/lo split of an exact value: lossless
     }
 }
 
-__global__ void __launch_bounds__(256) upsample2x_kernel(const __half* __restrict__ src, int n, int h, int w, int c, int ld_src,
-                                                         __half* __restrict__ dst, int ld_dst) {
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __half* __restrict__ src, int n, int h, int w, int c, int ld_src, int lo_src,
+                                                         __half* __restrict__ dst, int ld_dst, int lo_dst) {
     const int ho = 2 * h, wo = 2 * w, c8 = c / 8;
     const size_t total = (size_t)n * ho * wo * c8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int cc = (int)(i % c8); size_t t = i / c8;
         const int xo = (int)(t % wo); t /= wo;
         const int yo = (int)(t % ho); const int img = (int)(t / ho);
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (((size_t)img * h + yo / 2) * w + xo / 2) * ld_src + 8 * cc));
-        *reinterpret_cast<uint4*>(dst + (((size_t)img * ho + yo) * wo + xo) * ld_dst + 8 * cc) = v;
+        const __half* sp = src + (((size_t)img * h + yo / 2) * w + xo / 2) * ld_src + 8 * cc;
+        __half* dp = dst + (((size_t)img * ho + yo) * wo + xo) * ld_dst + 8 * cc;
+        *reinterpret_cast<uint4*>(dp) = __ldg(reinterpret_cast<const uint4*>(sp));
+        if (lo_src) *reinterpret_cast<uint4*>(dp + lo_dst) = __ldg(reinterpret_cast<const uint4*>(sp + lo_src));
     }
 }
 
 // ------------------------------------------------------------------------------------------------ attention gate
 // a [P][f_int] (already ReLU'd), x [P][ld_x] (first f_l channels), out [P][ld_dst] channels [c_off, c_off+f_l)
 // GS lanes cooperate on one pixel (GS = min(32, f_l/8)), 32/GS pixels per warp iteration.
-__global__ void __launch_bounds__(256) att_gate_kernel(const __half* __restrict__ a, int f_int, const __half* __restrict__ x, int f_l,
-                                                       int ld_x, const float* __restrict__ w_psi, float psi_scale, float psi_shift,
-                                                       __half* __restrict__ dst, int ld_dst, int c_off, size_t npix, int gs) {
+__global__ void __launch_bounds__(256) att_gate_kernel(const __half* __restrict__ a, int f_int, int ld_a, int lo_a,
+                                                       const __half* __restrict__ x, int f_l, int ld_x, int lo_x,
+                                                       const float* __restrict__ w_psi, float psi_scale, float psi_shift,
+                                                       __half* __restrict__ dst, int ld_dst, int c_off, int lo_dst, size_t npix, int gs) {
     extern __shared__ float s_wp[];
     for (int i = threadIdx.x; i < f_int; i += blockDim.x) s_wp[i] = w_psi[i];
     __syncthreads();
@@ -128,33 +153,26 @@ __global__ void __launch_bounds__(256) att_gate_kernel(const __half* __restrict_
         const bool live = pix < npix;
         float dot = 0.0f;
         if (live) {
-            const uint4* ap = reinterpret_cast<const uint4*>(a + pix * f_int);
+            const __half* ap = a + pix * ld_a;
             for (int ch = gl; ch < f_int / 8; ch += gs) {
-                const uint4 q = __ldg(ap + ch);
-                const __half2* hq = reinterpret_cast<const __half2*>(&q);
+                float f[8];
+                load8(ap + 8 * ch, lo_a, f);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 f = __half22float2(hq[j]);
-                    dot = fmaf(f.x, s_wp[8 * ch + 2 * j], dot);
-                    dot = fmaf(f.y, s_wp[8 * ch + 2 * j + 1], dot);
-                }
+                for (int j = 0; j < 8; ++j) dot = fmaf(f[j], s_wp[8 * ch + j], dot);
             }
         }
         for (int d = gs >> 1; d > 0; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d);
         const float z = fmaf(dot, psi_scale, psi_shift);
-        const float psi = 1.0f / (1.0f + __expf(-z));
+        const float psi = 1.0f / (1.0f + expf(-z));
         if (live) {
-            const uint4* xp = reinterpret_cast<const uint4*>(x + pix * ld_x);
-            uint4* op = reinterpret_cast<uint4*>(dst + pix * ld_dst + c_off);
+            const __half* xp = x + pix * ld_x;
+            __half* op = dst + pix * ld_dst + c_off;
             for (int ch = gl; ch < f_l / 8; ch += gs) {
-                uint4 q = __ldg(xp + ch);
-                __half2* hq = reinterpret_cast<__half2*>(&q);
+                float f[8];
+                load8(xp + 8 * ch, lo_x, f);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 f = __half22float2(hq[j]);
-                    hq[j] = __floats2half2_rn(f.x * psi, f.y * psi);
-                }
-                op[ch] = q;
+                for (int j = 0; j < 8; ++j) f[j] *= psi;
+                store8(op + 8 * ch, lo_dst, f);
             }
         }
     }
@@ -162,7 +180,7 @@ __global__ void __launch_bounds__(256) att_gate_kernel(const __half* __restrict_
 
 // ------------------------------------------------------------------------------------------------ small-N 1x1 head
 template <int COUT>
-__global__ void __launch_bounds__(256) conv1x1_head_kernel(const __half* __restrict__ src, int c_in, int ld_src,
+__global__ void __launch_bounds__(256) conv1x1_head_kernel(const __half* __restrict__ src, int c_in, int ld_src, int lo_src,
                                                            const float* __restrict__ wt,     // [COUT][c_in]
                                                            const float* __restrict__ bias, int sigmoid,
                                                            float* __restrict__ dst, int n, size_t hw) {
@@ -174,13 +192,10 @@ __global__ void __launch_bounds__(256) conv1x1_head_kernel(const __half* __restr
         float acc[COUT];
 #pragma unroll
         for (int c = 0; c < COUT; ++c) acc[c] = bias[c];
-        const uint4* sp = reinterpret_cast<const uint4*>(src + pix * ld_src);
+        const __half* sp = src + pix * ld_src;
         for (int ch = 0; ch < c_in / 8; ++ch) {
-            const uint4 q = __ldg(sp + ch);
-            const __half2* hq = reinterpret_cast<const __half2*>(&q);
             float f[8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { const float2 t = __half22float2(hq[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+            load8(sp + 8 * ch, lo_src, f);
 #pragma unroll
             for (int c = 0; c < COUT; ++c) {
                 const float* wr = s_w + c * c_in + 8 * ch;
@@ -192,7 +207,7 @@ __global__ void __launch_bounds__(256) conv1x1_head_kernel(const __half* __restr
 #pragma unroll
         for (int c = 0; c < COUT; ++c) {
             float v = acc[c];
-            if (sigmoid) v = 1.0f / (1.0f + __expf(-v));
+            if (sigmoid) v = 1.0f / (1.0f + expf(-v));
             dst[(img * COUT + c) * hw + rem] = v;
         }
     }
@@ -209,78 +224,90 @@ static int grid_for(size_t work_items, int threads, int per_thread = 1) {
 
 using namespace nbp;
 
+static int check_plane(const char* who, int c, int ld, int lo) {
+    if (lo < 0 || lo % 8 || (lo > 0 && lo < c) || ld < lo + c || ld % 8) return invalid("%s: bad plane layout c=%d ld=%d lo=%d", who, c, ld, lo);
+    return NBP_OK;
+}
+
 extern "C" int nbp_conv_first(const float* x, int n, int c_in, int h, int w, const float* weight, const float* scale,
-                              const float* shift, int c_out, void* dst, int dst_ld, void* stream) {
+                              const float* shift, int c_out, void* dst, int dst_ld, int dst_lo, void* stream) {
     if (!x || !weight || !scale || !shift || !dst) return invalid("nbp_conv_first: null pointer argument");
     if (n <= 0 || h <= 0 || w <= 0 || c_in <= 0 || c_in > 16) return invalid("nbp_conv_first: bad sizes n=%d c_in=%d h=%d w=%d", n, c_in, h, w);
     if (c_out != 64) return invalid("nbp_conv_first: c_out must be 64 (got %d)", c_out);
-    if (dst_ld < c_out || dst_ld % 8 || ((uintptr_t)dst & 15)) return invalid("nbp_conv_first: bad destination layout");
+    int rc = check_plane("nbp_conv_first", c_out, dst_ld, dst_lo);
+    if (rc) return rc;
+    if ((uintptr_t)dst & 15) return invalid("nbp_conv_first: dst must be 16-byte aligned");
     const size_t smem = sizeof(float) * (size_t)(9 * c_in * 64 + 128);
-    static bool attr = false;
-    if (!attr) {
-        int rc = check_cuda(cudaFuncSetAttribute(conv_first_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 16 * 64 * 4 + 512),
-                            "cudaFuncSetAttribute(conv_first)");
-        if (rc) return rc;
-        attr = true;
-    }
     conv_first_kernel<64><<<grid_for((size_t)n * h * w, 128), 128, smem, (cudaStream_t)stream>>>(x, n, c_in, h, w, weight, scale, shift,
-                                                                                                  (__half*)dst, dst_ld);
+                                                                                                  (__half*)dst, dst_ld, dst_lo);
     count_launch();
     return check_cuda(cudaGetLastError(), "nbp_conv_first launch");
 }
 
-static int check_nhwc(const char* who, const void* src, const void* dst, int n, int h, int w, int c, int ld_src, int ld_dst) {
+static int check_nhwc(const char* who, const void* src, const void* dst, int n, int h, int w, int c, int ld_src, int lo_src, int ld_dst, int lo_dst) {
     if (!src || !dst) return invalid("%s: null pointer argument", who);
     if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || c % 8) return invalid("%s: bad sizes n=%d h=%d w=%d c=%d (c must be a multiple of 8)", who, n, h, w, c);
-    if (ld_src < c || ld_dst < c || ld_src % 8 || ld_dst % 8) return invalid("%s: channel strides must be >= c and multiples of 8", who);
+    int rc = check_plane(who, c, ld_src, lo_src);
+    if (rc) return rc;
+    rc = check_plane(who, c, ld_dst, lo_dst);
+    if (rc) return rc;
+    if ((lo_src == 0) != (lo_dst == 0)) return invalid("%s: source and destination must use the same format", who);
     if (((uintptr_t)src | (uintptr_t)dst) & 15) return invalid("%s: pointers must be 16-byte aligned", who);
     return NBP_OK;
 }
 
-extern "C" int nbp_maxpool2x2(const void* src, int n, int h, int w, int c, int ld_src, void* dst, int ld_dst, void* stream) {
-    int rc = check_nhwc("nbp_maxpool2x2", src, dst, n, h, w, c, ld_src, ld_dst);
+extern "C" int nbp_maxpool2x2(const void* src, int n, int h, int w, int c, int ld_src, int lo_src, void* dst, int ld_dst, int lo_dst, void* stream) {
+    int rc = check_nhwc("nbp_maxpool2x2", src, dst, n, h, w, c, ld_src, lo_src, ld_dst, lo_dst);
     if (rc) return rc;
     if ((h | w) & 1) return invalid("nbp_maxpool2x2: h and w must be even");
     maxpool2x2_kernel<<<grid_for((size_t)n * (h / 2) * (w / 2) * (c / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __half*)src, n, h, w, c, ld_src, (__half*)dst, ld_dst);
+        (const __half*)src, n, h, w, c, ld_src, lo_src, (__half*)dst, ld_dst, lo_dst);
     count_launch();
     return check_cuda(cudaGetLastError(), "nbp_maxpool2x2 launch");
 }
 
-extern "C" int nbp_upsample2x(const void* src, int n, int h, int w, int c, int ld_src, void* dst, int ld_dst, void* stream) {
-    int rc = check_nhwc("nbp_upsample2x", src, dst, n, h, w, c, ld_src, ld_dst);
+extern "C" int nbp_upsample2x(const void* src, int n, int h, int w, int c, int ld_src, int lo_src, void* dst, int ld_dst, int lo_dst, void* stream) {
+    int rc = check_nhwc("nbp_upsample2x", src, dst, n, h, w, c, ld_src, lo_src, ld_dst, lo_dst);
     if (rc) return rc;
     upsample2x_kernel<<<grid_for((size_t)n * h * w * 4 * (c / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __half*)src, n, h, w, c, ld_src, (__half*)dst, ld_dst);
+        (const __half*)src, n, h, w, c, ld_src, lo_src, (__half*)dst, ld_dst, lo_dst);
     count_launch();
     return check_cuda(cudaGetLastError(), "nbp_upsample2x launch");
 }
 
-extern "C" int nbp_att_gate(const void* a, int f_int, const void* x, int f_l, int ld_x, const float* w_psi, float psi_scale,
-                            float psi_shift, void* dst, int dst_ld, int dst_c_off, int64_t npix, void* stream) {
+extern "C" int nbp_att_gate(const void* a, int f_int, int ld_a, int lo_a, const void* x, int f_l, int ld_x, int lo_x,
+                            const float* w_psi, float psi_scale, float psi_shift,
+                            void* dst, int dst_ld, int dst_c_off, int dst_lo, int64_t npix, void* stream) {
     if (!a || !x || !w_psi || !dst) return invalid("nbp_att_gate: null pointer argument");
     if (f_int <= 0 || f_int % 8 || f_l <= 0 || f_l % 8 || npix <= 0) return invalid("nbp_att_gate: bad sizes f_int=%d f_l=%d npix=%lld", f_int, f_l, (long long)npix);
-    if (ld_x < f_l || ld_x % 8 || dst_ld % 8 || dst_c_off % 8 || dst_c_off + f_l > dst_ld) return invalid("nbp_att_gate: bad channel layout");
+    int rc = check_plane("nbp_att_gate(a)", f_int, ld_a, lo_a);
+    if (rc) return rc;
+    rc = check_plane("nbp_att_gate(x)", f_l, ld_x, lo_x);
+    if (rc) return rc;
+    if (dst_ld % 8 || dst_c_off % 8 || dst_lo % 8 || dst_c_off + dst_lo + f_l > dst_ld) return invalid("nbp_att_gate: bad destination layout");
     if (((uintptr_t)a | (uintptr_t)x | (uintptr_t)dst) & 15) return invalid("nbp_att_gate: pointers must be 16-byte aligned");
     int gs = 1;
     while (gs * 2 <= 32 && gs * 2 <= f_l / 8) gs *= 2;
     const size_t warps = ((size_t)npix + (32 / gs) - 1) / (32 / gs);
     att_gate_kernel<<<grid_for(warps * 32, 256, 2), 256, sizeof(float) * f_int, (cudaStream_t)stream>>>(
-        (const __half*)a, f_int, (const __half*)x, f_l, ld_x, w_psi, psi_scale, psi_shift, (__half*)dst, dst_ld, dst_c_off, (size_t)npix, gs);
+        (const __half*)a, f_int, ld_a, lo_a, (const __half*)x, f_l, ld_x, lo_x, w_psi, psi_scale, psi_shift,
+        (__half*)dst, dst_ld, dst_c_off, dst_lo, (size_t)npix, gs);
     count_launch();
     return check_cuda(cudaGetLastError(), "nbp_att_gate launch");
 }
 
-extern "C" int nbp_conv1x1_head(const void* src, int c_in, int ld_src, const float* weight, const float* bias, int c_out,
+extern "C" int nbp_conv1x1_head(const void* src, int c_in, int ld_src, int lo_src, const float* weight, const float* bias, int c_out,
                                 int sigmoid, float* dst, int n, int64_t hw, void* stream) {
     if (!src || !weight || !bias || !dst) return invalid("nbp_conv1x1_head: null pointer argument");
-    if (c_in <= 0 || c_in % 8 || ld_src < c_in || ld_src % 8 || n <= 0 || hw <= 0) return invalid("nbp_conv1x1_head: bad sizes");
+    if (c_in <= 0 || c_in % 8 || n <= 0 || hw <= 0) return invalid("nbp_conv1x1_head: bad sizes");
+    int rc = check_plane("nbp_conv1x1_head", c_in, ld_src, lo_src);
+    if (rc) return rc;
     if ((uintptr_t)src & 15) return invalid("nbp_conv1x1_head: src must be 16-byte aligned");
     const size_t smem = sizeof(float) * (size_t)c_out * c_in;
     const int g = grid_for((size_t)n * hw, 256);
     cudaStream_t st = (cudaStream_t)stream;
-    if (c_out == 8) conv1x1_head_kernel<8><<<g, 256, smem, st>>>((const __half*)src, c_in, ld_src, weight, bias, sigmoid, dst, n, (size_t)hw);
-    else if (c_out == 1) conv1x1_head_kernel<1><<<g, 256, smem, st>>>((const __half*)src, c_in, ld_src, weight, bias, sigmoid, dst, n, (size_t)hw);
+    if (c_out == 8) conv1x1_head_kernel<8><<<g, 256, smem, st>>>((const __half*)src, c_in, ld_src, lo_src, weight, bias, sigmoid, dst, n, (size_t)hw);
+    else if (c_out == 1) conv1x1_head_kernel<1><<<g, 256, smem, st>>>((const __half*)src, c_in, ld_src, lo_src, weight, bias, sigmoid, dst, n, (size_t)hw);
     else return invalid("nbp_conv1x1_head: c_out must be 1 or 8 (got %d)", c_out);
     count_launch();
     return check_cuda(cudaGetLastError(), "nbp_conv1x1_head launch");

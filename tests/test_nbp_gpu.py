@@ -23,26 +23,53 @@ def _st():
     return torch.cuda.current_stream().cuda_stream
 
 
-def _nhwc16(t):      # NCHW fp32 -> NHWC fp16 contiguous
-    return t.permute(0, 2, 3, 1).contiguous().to(torch.float16)
+def _split(t):
+    hi = t.to(torch.float16)
+    lo = ((t - hi.float()) * 2048.0).to(torch.float16)
+    return hi, lo
 
 
-def _run_conv(x0, w, scale, shift, relu, taps, x1=None, dst_ld=None, dst_off=0):
-    """x0/x1 NCHW fp32 (values already fp16-representable), w (Cout, Cin, k, k) fp32."""
+def _to_act(x, precise):
+    """NCHW fp32 -> NHWC fp16 device tensor [n,h,w,planes*c] (+ c, ld, lo)."""
+    a = x.permute(0, 2, 3, 1).contiguous()
+    c = a.shape[-1]
+    if precise:
+        hi, lo = _split(a)
+        return torch.cat((hi, lo), dim=-1).contiguous().to(DEV), c, 2 * c, c
+    return a.to(torch.float16).to(DEV), c, c, 0
+
+
+def _from_act(t, c, lo):
+    t = t.float().cpu()
+    return t[..., :c] + (t[..., lo:lo + c] / 2048.0 if lo else 0.0)
+
+
+def _pack_w(w2d, precise):
+    from nextbestpath_b200.networks.nbp_model import _pack_gemm_weight
+    return _pack_gemm_weight(w2d, precise).to(DEV)
+
+
+def _run_conv(x0, w, scale, shift, relu, taps, precise, x1=None, extra=0, dst_off=0):
+    """x0/x1 NCHW fp32, w (Cout, Cin, k, k) fp32.  The destination holds `extra` more channels than cout and the
+    result is written at channel `dst_off` (concat fusion); untouched elements keep the fill value 7."""
     n, c0, h, wd = x0.shape
-    c1 = 0 if x1 is None else x1.shape[1]
     cout = w.shape[0]
-    a0 = _nhwc16(x0).to(DEV)
-    a1 = _nhwc16(x1).to(DEV) if x1 is not None else None
-    wp = w.permute(0, 2, 3, 1).reshape(cout, -1).to(torch.float16).contiguous().to(DEV)
-    ld = dst_ld or cout
-    out = torch.full((n, h, wd, ld), 7.0, dtype=torch.float16, device=DEV)
+    a0, c0, ld0, lo0 = _to_act(x0, precise)
+    if x1 is not None:
+        a1, c1, ld1, lo1 = _to_act(x1, precise)
+    else:
+        a1, c1, ld1, lo1 = None, 0, 0, 0
+    wp = _pack_w(w.permute(0, 2, 3, 1).reshape(cout, -1), precise)
+    ctot = cout + extra
+    planes = 2 if precise else 1
+    out = torch.full((n, h, wd, planes * ctot), 7.0, dtype=torch.float16, device=DEV)
     sc, sh = scale.to(DEV).contiguous(), shift.to(DEV).contiguous()
-    d = _lib.ConvDesc(a0.data_ptr(), c0, c0, a1.data_ptr() if a1 is not None else None, c1, c1, n, h, wd, taps,
-                      wp.data_ptr(), cout, sc.data_ptr(), sh.data_ptr(), int(relu), out.data_ptr(), ld, dst_off)
+    d = _lib.ConvDesc(int(precise), a0.data_ptr(), c0, ld0, lo0, a1.data_ptr() if a1 is not None else None, c1, ld1, lo1,
+                      n, h, wd, taps, wp.data_ptr(), cout, sc.data_ptr(), sh.data_ptr(), int(relu),
+                      out.data_ptr(), planes * ctot, dst_off, ctot if precise else 0)
     _lib.check(_lib.lib().nbp_conv_fwd(ctypes.byref(d), _st()), "nbp_conv_fwd")
     torch.cuda.synchronize()
-    return out.float().cpu()
+    return out.cpu(), ctot
 
 
 CASES = [
@@ -59,10 +86,13 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("precise", [True, False])
 @pytest.mark.parametrize("n,h,w,c0,c1,cout,taps", CASES)
-def test_conv_fwd_matches_fp32_reference(n, h, w, c0, c1, cout, taps):
+def test_conv_fwd_matches_fp64_reference(n, h, w, c0, c1, cout, taps, precise):
     g = torch.Generator().manual_seed(n * 1000 + h + c0 + cout + taps)
-    q = lambda t: t.to(torch.float16).float()
+    # fast mode is tested on fp16-representable data (so only the output rounding remains);
+    # precise mode on arbitrary fp32 data: the fp16x2 split must carry (almost) all of it
+    q = (lambda t: t) if precise else (lambda t: t.to(torch.float16).float())
     x0 = q(torch.randn(n, c0, h, w, generator=g))
     x1 = q(torch.randn(n, c1, h, w, generator=g)) if c1 else None
     k = 3 if taps == 9 else 1
@@ -71,68 +101,86 @@ def test_conv_fwd_matches_fp32_reference(n, h, w, c0, c1, cout, taps):
     shift = torch.randn(cout, generator=g) * 0.1
     xin = x0 if x1 is None else torch.cat((x0, x1), 1)
     ref = F.conv2d(xin.double(), wt.double(), padding=k // 2) * scale.double()[None, :, None, None] + shift.double()[None, :, None, None]
+    # precise: fp32-grade (tensor-core fp32 accumulation over K up to 9216 terms); fast: fp16 output rounding (2^-11)
+    tol = 2e-5 if precise else 1.5e-3
     for relu in (True, False):
         r = (F.relu(ref) if relu else ref).permute(0, 2, 3, 1).float()
-        out = _run_conv(x0, wt, scale, shift, relu, taps, x1=x1)
-        err = (out - r).abs().max().item()
-        # fp16 output rounding (2^-11 relative) + fp32 accumulation order
-        assert err <= 1.5e-3 * max(1.0, r.abs().max().item()), f"max err {err}"
+        out, ctot = _run_conv(x0, wt, scale, shift, relu, taps, precise, x1=x1)
+        got = _from_act(out, cout, ctot if precise else 0)
+        err = (got - r).abs().max().item()
+        assert err <= tol * max(1.0, r.abs().max().item()), f"max err {err}"
     # destination with a channel offset inside a wider buffer; untouched channels keep their value
-    out = _run_conv(x0, wt, scale, shift, True, taps, x1=x1, dst_ld=cout + 64, dst_off=32 if cout % 32 == 0 else 0)
+    out, ctot = _run_conv(x0, wt, scale, shift, True, taps, precise, x1=x1, extra=64, dst_off=32)
     r = F.relu(ref).permute(0, 2, 3, 1).float()
-    assert (out[..., 32:32 + cout] - r).abs().max().item() <= 1.5e-3 * max(1.0, r.abs().max().item())
-    assert (out[..., :32] == 7.0).all() and (out[..., 32 + cout:] == 7.0).all()
+    planes = 2 if precise else 1
+    for pl in range(planes):
+        blk = out[..., pl * ctot:(pl + 1) * ctot].float()
+        assert (blk[..., :32] == 7.0).all() and (blk[..., 32 + cout:] == 7.0).all()
+    got = out[..., 32:32 + cout].float() + (out[..., ctot + 32:ctot + 32 + cout].float() / 2048.0 if precise else 0.0)
+    assert (got - r).abs().max().item() <= tol * max(1.0, r.abs().max().item())
 
 
-def test_pointwise_kernels_match_torch():
+@pytest.mark.parametrize("precise", [True, False])
+def test_pointwise_kernels_match_torch(precise):
     L = _lib.lib()
     g = torch.Generator().manual_seed(3)
-    x = torch.randn(3, 64, 12, 20, generator=g).to(torch.float16)
-    a = x.permute(0, 2, 3, 1).contiguous().to(DEV)
-    # maxpool
-    p = torch.empty((3, 6, 10, 64), dtype=torch.float16, device=DEV)
-    _lib.check(L.nbp_maxpool2x2(a.data_ptr(), 3, 12, 20, 64, 64, p.data_ptr(), 64, _st()), "pool")
-    assert torch.equal(p.cpu().permute(0, 3, 1, 2), F.max_pool2d(x.float(), 2, 2).to(torch.float16))
-    # upsample
-    u = torch.empty((3, 24, 40, 64), dtype=torch.float16, device=DEV)
-    _lib.check(L.nbp_upsample2x(a.data_ptr(), 3, 12, 20, 64, 64, u.data_ptr(), 64, _st()), "up")
-    assert torch.equal(u.cpu().permute(0, 3, 1, 2), F.interpolate(x.float(), scale_factor=2, mode="nearest").to(torch.float16))
+    q = (lambda t: t) if precise else (lambda t: t.to(torch.float16).float())
+    tol = 2e-5 if precise else 1.5e-3
+    x = q(torch.randn(3, 64, 12, 20, generator=g))
+    a, c, ld, lo = _to_act(x, precise)
+    planes = 2 if precise else 1
+    # maxpool (exact in both formats: max of representable values)
+    p = torch.empty((3, 6, 10, planes * 64), dtype=torch.float16, device=DEV)
+    _lib.check(L.nbp_maxpool2x2(a.data_ptr(), 3, 12, 20, 64, ld, lo, p.data_ptr(), ld, lo, _st()), "pool")
+    want = F.max_pool2d(_from_act(a, 64, lo).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    assert torch.equal(_from_act(p, 64, lo), want)
+    # upsample (a copy)
+    u = torch.empty((3, 24, 40, planes * 64), dtype=torch.float16, device=DEV)
+    _lib.check(L.nbp_upsample2x(a.data_ptr(), 3, 12, 20, 64, ld, lo, u.data_ptr(), ld, lo, _st()), "up")
+    want = F.interpolate(_from_act(a, 64, lo).permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(_from_act(u, 64, lo), want)
     # attention gate for several group sizes
     for f_int, f_l in ((32, 64), (64, 128), (256, 512), (128, 256)):
         npix = 333
-        av = torch.rand(npix, f_int, generator=g).to(torch.float16)
-        xv = torch.randn(npix, f_l, generator=g).to(torch.float16)
+        av = q(torch.rand(npix, f_int, generator=g))
+        xv = q(torch.randn(npix, f_l, generator=g))
         wp = torch.randn(f_int, generator=g) / f_int ** 0.5
-        dst = torch.zeros((npix, 2 * f_l), dtype=torch.float16, device=DEV)
-        ad, xd, wd = av.to(DEV), xv.to(DEV), wp.to(DEV)
-        _lib.check(L.nbp_att_gate(ad.data_ptr(), f_int, xd.data_ptr(), f_l, f_l, wd.data_ptr(), 1.3, -0.2, dst.data_ptr(),
-                                  2 * f_l, 0, npix, _st()), "gate")
-        psi = torch.sigmoid((av.float() @ wp) * 1.3 - 0.2)
-        ref = xv.float() * psi[:, None]
-        got = dst.cpu().float()
-        assert (got[:, :f_l] - ref).abs().max() <= 2e-3 * ref.abs().max() and (got[:, f_l:] == 0).all()
+        ad, _, ld_a, lo_a = _to_act(av.view(1, npix, 1, f_int).permute(0, 3, 1, 2), precise)
+        xd, _, ld_x, lo_x = _to_act(xv.view(1, npix, 1, f_l).permute(0, 3, 1, 2), precise)
+        ctot = 2 * f_l
+        dst = torch.zeros((npix, planes * ctot), dtype=torch.float16, device=DEV)
+        wd = wp.to(DEV)
+        _lib.check(L.nbp_att_gate(ad.data_ptr(), f_int, ld_a, lo_a, xd.data_ptr(), f_l, ld_x, lo_x, wd.data_ptr(), 1.3, -0.2,
+                                  dst.data_ptr(), planes * ctot, 0, ctot if precise else 0, npix, _st()), "gate")
+        psi = torch.sigmoid((av.double() @ wp.double()) * 1.3 - 0.2)
+        ref = (xv.double() * psi[:, None]).float()
+        got = _from_act(dst, f_l, ctot if precise else 0)
+        assert (got - ref).abs().max() <= tol * ref.abs().max()
+        assert (dst.cpu()[:, f_l:ctot] == 0).all()
     # heads
     for cout, sig in ((8, 0), (1, 1)):
         cin = 256 if cout == 8 else 64
-        src = torch.randn(2, 9, 7, cin, generator=g).to(torch.float16)
+        src = q(torch.randn(2, cin, 9, 7, generator=g))
         w = torch.randn(cout, cin, generator=g) / cin ** 0.5
         b = torch.randn(cout, generator=g)
         out = torch.empty((2, cout, 9, 7), device=DEV)
-        sd, wd_, bd = src.to(DEV), w.to(DEV), b.to(DEV)
-        _lib.check(L.nbp_conv1x1_head(sd.data_ptr(), cin, cin, wd_.data_ptr(), bd.data_ptr(), cout, sig, out.data_ptr(), 2, 63, _st()), "head")
-        ref = torch.einsum("nhwc,oc->nohw", src.float(), w) + b[None, :, None, None]
-        ref = torch.sigmoid(ref) if sig else ref
-        assert (out.cpu() - ref).abs().max() <= 1e-4 * max(1.0, ref.abs().max())
+        sd_, _, ld_s, lo_s = _to_act(src, precise)
+        wd_, bd = w.to(DEV), b.to(DEV)
+        _lib.check(L.nbp_conv1x1_head(sd_.data_ptr(), cin, ld_s, lo_s, wd_.data_ptr(), bd.data_ptr(), cout, sig, out.data_ptr(), 2, 63, _st()), "head")
+        ref = torch.einsum("nchw,oc->nohw", src.double(), w.double()) + b.double()[None, :, None, None]
+        ref = (torch.sigmoid(ref) if sig else ref).float()
+        assert (out.cpu() - ref).abs().max() <= 3e-6 * max(1.0, ref.abs().max())
     # stem: fp32 count image -> NHWC fp16
     xin = NT.count_like_input(2, 32, seed=1)
     w0 = torch.randn(64, 5, 3, 3, generator=g) * 0.1
     sc, sh = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1
-    dst = torch.empty((2, 32, 32, 64), dtype=torch.float16, device=DEV)
+    dst = torch.empty((2, 32, 32, planes * 64), dtype=torch.float16, device=DEV)
     wp = w0.permute(2, 3, 1, 0).reshape(45, 64).contiguous().to(DEV)
     xd, scd, shd = xin.to(DEV), sc.to(DEV), sh.to(DEV)
-    _lib.check(L.nbp_conv_first(xd.data_ptr(), 2, 5, 32, 32, wp.data_ptr(), scd.data_ptr(), shd.data_ptr(), 64, dst.data_ptr(), 64, _st()), "stem")
-    ref = F.relu(F.conv2d(xin, w0, padding=1) * sc[None, :, None, None] + sh[None, :, None, None]).permute(0, 2, 3, 1)
-    assert (dst.cpu().float() - ref).abs().max() <= 1e-3 * ref.abs().max()
+    _lib.check(L.nbp_conv_first(xd.data_ptr(), 2, 5, 32, 32, wp.data_ptr(), scd.data_ptr(), shd.data_ptr(), 64, dst.data_ptr(),
+                                planes * 64, 64 if precise else 0, _st()), "stem")
+    ref = F.relu(F.conv2d(xin.double(), w0.double(), padding=1) * sc.double()[None, :, None, None] + sh.double()[None, :, None, None]).permute(0, 2, 3, 1).float()
+    assert (_from_act(dst, 64, 64 if precise else 0) - ref).abs().max() <= (3e-6 if precise else 1e-3) * ref.abs().max()
 
 
 def _errs(a, b):
@@ -142,10 +190,12 @@ def _errs(a, b):
 
 @pytest.mark.parametrize("B,S", [(1, 128), (3, 64), (2, 256)])
 def test_nbp_forward_matches_fp32_oracle(B, S):
+    """The parity path (precision "fp16x2").  config[0] of BASELINE.json is (B=1, S=128)."""
     sd = NT.golden_state_dict(seed=9)
     net = NBP()
     net.load_state_dict(sd)
     net.to(DEV).eval()
+    assert net.precision == "fp16x2"
     x = NT.count_like_input(B, S, seed=3)
     with torch.no_grad():
         o1, o2 = net(x.to(DEV))
@@ -173,6 +223,22 @@ def test_nbp_forward_matches_reference_fixture(golden_dir):
     m1, l1, mae1 = _errs(o1.cpu(), torch.from_numpy(g["out1"]))
     m2, l2, mae2 = _errs(o2.cpu(), torch.from_numpy(g["out2"]))
     assert m1 <= 1e-3 and l1 <= 1e-3 and mae1 < 1e-3 and m2 <= 1e-3 and mae2 < 1e-3
+
+
+def test_nbp_fast_fp16_mode_error_is_as_documented():
+    """precision "fp16": one tensor-core pass instead of three; the error is what fp16 (or tf32) storage gives on
+    BN-calibrated weights -- about 7e-3 -- and is NOT the parity path."""
+    sd = NT.golden_state_dict(seed=9)
+    net = NBP(); net.load_state_dict(sd); net.to(DEV).eval()
+    net.precision = "fp16"
+    x = NT.count_like_input(1, 128, seed=3)
+    with torch.no_grad():
+        o1, o2 = net(x.to(DEV))
+        r1, r2 = NT.forward(sd, x)
+    m1, l1, _ = _errs(o1.cpu(), r1)
+    m2, l2, _ = _errs(o2.cpu(), r2)
+    print(f"fp16 fast mode: out1 max-rel {m1:.2e} l2-rel {l1:.2e} | out2 max-rel {m2:.2e} l2-rel {l2:.2e}")
+    assert 1e-4 < l1 < 3e-2 and l2 < 5e-2
 
 
 def test_nbp_chunking_and_errors():
