@@ -65,8 +65,9 @@ int nbp_raster_depth_batched(const float* verts, const int32_t* faces,
  * (macarons_utils.py:2811-2847, :2788-2809, NDC tables :2270-2279) and the growing
  * torch.vstack((full_pc, part_pc)) at next_best_path/testers/nbp_planning.py:105,352.
  *
- * Frame f (zbuf[f], R[f], T[f]) belongs to cloud frame_scene[f].  A pixel is valid when
- * zbuf > -1 (and mask != 0 when mask is given) and zbuf < fov_range (fov_range <= 0: no range test).
+ * Frame f (zbuf[f], R[f], T[f]) belongs to cloud frame_scene[f].  A pixel is valid when mask != 0 -- mask NULL
+ * means the stored frame mask zbuf > -1 (macarons_utils.py:2771) -- and zbuf < fov_range (fov_range <= 0: no
+ * range test), i.e. points_mask = mask * (depth < fov_range) of macarons_utils.py:2825.
  * Of the n valid pixels of a frame, k = (int)(n * gathering_factor) are kept:
  *   gathering_factor >= 1 : all of them, in row-major pixel order (the parity path: the caller applies
  *                           torch.randperm(n)[:k] itself, exactly as macarons_utils.py:2837);
@@ -146,6 +147,12 @@ typedef struct nbp_conv_desc {
 int nbp_conv_fwd(const nbp_conv_desc* desc, void* stream);
 /* The pointwise kernels below take, for every NHWC fp16 tensor, the pixel stride `ld` (elements) and the
  * offset `lo` of the lo plane of the fp16x2 format (0 = single-plane fp16 tensor). */
+/* Measurement aid for bench.py (not part of the data path): between _begin and _end every conv_gemm launch is
+ * bracketed by CUDA events on its stream; _end waits for them and returns the summed device time, the summed
+ * ALGORITHMIC flops (2*M*N*K of the convolution, independent of the numeric mode) and the launch count.
+ * These two calls are the only ones in the library that create CUDA events / synchronise. */
+int nbp_conv_profile_begin(int max_launches);
+int nbp_conv_profile_end(double* total_ms_host, double* total_flops_host, uint64_t* launches_host, uint64_t* dropped_host);
 /* Conv1.conv.0: x fp32 NCHW [n,c_in,h,w] counts -> NHWC fp16; weight fp32 [9*c_in][c_out]
  * (tap-major, then input channel), c_out = 64; fused affine + ReLU (nbp_model.py:11-13) */
 int nbp_conv_first(const float* x, int n, int c_in, int h, int w, const float* weight, const float* scale,

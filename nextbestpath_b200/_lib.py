@@ -45,6 +45,8 @@ class ConvDesc(C.Structure):
 
 SIGNATURES.update({
     "nbp_conv_fwd": (_i, [C.POINTER(ConvDesc), _p]),
+    "nbp_conv_profile_begin": (_i, [_i]),
+    "nbp_conv_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "nbp_conv_first": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _i, _p]),
     "nbp_maxpool2x2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     "nbp_upsample2x": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),

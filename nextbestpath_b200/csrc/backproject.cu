@@ -60,8 +60,7 @@ struct BpParams {
 
 __device__ __forceinline__ bool pixel_valid(const BpParams& p, const float* z, const uint8_t* m, int i) {
     const float d = __ldg(z + i);
-    bool v = d > -1.0f;
-    if (m) v = v && (m[i] != 0);
+    bool v = m ? (m[i] != 0) : (d > -1.0f);       // an explicit mask replaces the default zbuf > -1 (macarons_utils.py:2771,2825)
     if (p.fov_range > 0.0f) v = v && (d < p.fov_range);
     return v;
 }

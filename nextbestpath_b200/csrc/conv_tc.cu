@@ -30,6 +30,8 @@
 //               so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
 
+#include <vector>
+
 #include "nbp_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -302,6 +304,16 @@ static int make_weight_map(CUtensorMap* m, const void* ptr, int k_total, int c_o
     return NBP_OK;
 }
 
+// ---- optional per-launch timing of conv_gemm_f16 (bench.py roofline): CUDA events recorded on the launch stream
+struct ConvProfile {
+    bool enabled = false;
+    std::vector<cudaEvent_t> ev;       // pairs (start, stop)
+    size_t used = 0;                   // events consumed
+    double flops = 0.0;                // algorithmic 2*M*N*K of the recorded launches
+    uint64_t dropped = 0;
+};
+static ConvProfile g_prof;
+
 static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 static int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
 
@@ -317,7 +329,15 @@ static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
     }
     const int tiles = kp.m_tiles * kp.n_tiles;
     const int grid = tiles < sms ? tiles : sms;
+    const bool prof = g_prof.enabled && g_prof.used + 2 <= g_prof.ev.size();
+    if (g_prof.enabled && !prof) ++g_prof.dropped;
+    if (prof) cudaEventRecord(g_prof.ev[g_prof.used], st);
     conv_gemm_f16<BLOCK_N, PRECISE><<<grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b, kp);
+    if (prof) {
+        cudaEventRecord(g_prof.ev[g_prof.used + 1], st);
+        g_prof.used += 2;
+        g_prof.flops += 2.0 * (double)kp.n * kp.h * kp.w * (double)(kp.n_tiles * BLOCK_N) * (double)(kp.taps * (kp.kc0 + kp.kc1) * BLOCK_K);
+    }
     count_launch();
     return check_cuda(cudaGetLastError(), "conv_gemm_f16 launch");
 }
@@ -392,4 +412,34 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
         case 64:  return launch_conv<64, false>(a0, a1, b, kp, sms, st);
         default:  return launch_conv<32, false>(a0, a1, b, kp, sms, st);
     }
+}
+
+extern "C" int nbp_conv_profile_begin(int max_launches) {
+    if (max_launches <= 0) return invalid("nbp_conv_profile_begin: max_launches must be positive");
+    while (g_prof.ev.size() < (size_t)2 * max_launches) {
+        cudaEvent_t e;
+        int rc = check_cuda(cudaEventCreate(&e), "cudaEventCreate");
+        if (rc) return rc;
+        g_prof.ev.push_back(e);
+    }
+    g_prof.used = 0; g_prof.flops = 0.0; g_prof.dropped = 0; g_prof.enabled = true;
+    return NBP_OK;
+}
+
+extern "C" int nbp_conv_profile_end(double* total_ms, double* total_flops, uint64_t* launches, uint64_t* dropped) {
+    g_prof.enabled = false;
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+        int rc = check_cuda(cudaEventSynchronize(g_prof.ev[i + 1]), "cudaEventSynchronize");
+        if (rc) return rc;
+        float t = 0.f;
+        rc = check_cuda(cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]), "cudaEventElapsedTime");
+        if (rc) return rc;
+        ms += t;
+    }
+    if (total_ms) *total_ms = ms;
+    if (total_flops) *total_flops = g_prof.flops;
+    if (launches) *launches = g_prof.used / 2;
+    if (dropped) *dropped = g_prof.dropped;
+    return NBP_OK;
 }

@@ -199,14 +199,14 @@ def unproject(zbuf, R, T, fov_deg: float = 60.0):
 
 
 def partial_point_cloud(zbuf, R, T, fov_range: float | None = 70.0, gathering_factor: float = 0.05,
-                        indices=None, fov_deg: float = 60.0):
+                        indices=None, fov_deg: float = 60.0, mask=None):
     """Camera.compute_partial_point_cloud macarons_utils.py:2811-2847.
     mask = (zbuf > -1) & (zbuf < fov_range); valid world points in row-major pixel order; keep
     k = int(n*gathering_factor) of them: ``indices`` (a permutation prefix, e.g.
     torch.randperm(n)[:k] as :2837) selects which; None with gathering_factor == 1 keeps all."""
     z = np.asarray(zbuf, dtype=np.float32)
     flat = z.reshape(-1)
-    mask = flat > f32(-1)
+    mask = (flat > f32(-1)) if mask is None else (np.asarray(mask).reshape(-1) != 0)
     if fov_range is not None:
         mask &= flat < f32(fov_range)
     pts = unproject(z, R, T, fov_deg)[mask]

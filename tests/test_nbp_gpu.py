@@ -108,6 +108,9 @@ def test_conv_fwd_matches_fp64_reference(n, h, w, c0, c1, cout, taps, precise):
         out, ctot = _run_conv(x0, wt, scale, shift, relu, taps, precise, x1=x1)
         got = _from_act(out, cout, ctot if precise else 0)
         err = (got - r).abs().max().item()
+        if relu:
+            print(f"conv K={taps * (c0 + c1)} N={cout} precise={precise}: max err {err:.2e} (ref max {r.abs().max().item():.2f}, "
+                  f"l2-rel {((got - r).norm() / r.norm()).item():.2e})")
         assert err <= tol * max(1.0, r.abs().max().item()), f"max err {err}"
     # destination with a channel offset inside a wider buffer; untouched channels keep their value
     out, ctot = _run_conv(x0, wt, scale, shift, True, taps, precise, x1=x1, extra=64, dst_off=32)
