@@ -185,7 +185,7 @@ def run_ours(args):
     import torch.distributed as dist
     from nextbestpath_b200 import _lib, ops
     from nextbestpath_b200.networks import NBP
-    from nextbestpath_b200.rollout import RolloutEngine
+    from nextbestpath_b200.rollout import RolloutEngine, shard_scenes
     from oracle import nbp_torch as NT            # only: golden weights + the cpu_baseline leg
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,9 +202,8 @@ def run_ours(args):
 
     S = args.grid
     B_total = args.scenes
-    per = [B_total // world + (1 if r < B_total % world else 0) for r in range(world)]
-    first = sum(per[:rank])
-    B = per[rank]
+    per = [shard_scenes(B_total, world, r)[1] for r in range(world)]
+    first, B = shard_scenes(B_total, world, rank)
     n_total = args.prefill + 2 * (args.warmup + args.steps) + 2
     scenes, poses, az = make_workload(B, args.level, n_total + 8, rank0_scene_index=first)
     sd = NT.golden_state_dict(seed=9)
@@ -225,12 +224,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        tt = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
+    from nextbestpath_b200.rollout import max_over_ranks as _mor
+    max_over_ranks = lambda x: _mor(x, dev)
 
     # ================= value: trajectory cameras resident in HBM
     n_run = args.warmup + args.steps
@@ -290,11 +285,16 @@ def run_ours(args):
 
     # ================= roofline of the dominant kernel
     peaks = load_peaks()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")      # from the committed `ncu --set full` capture
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch_mean")
     conv_ms, conv_flops = cms.value, cfl.value
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "conv_gemm_f16 (tcgen05.mma kind::f16, TMEM accumulators, TMA operands)",
                 "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
-                "traffic": None, "peak_source": peaks["which"],
+                "traffic": traffic, "traffic_source": "profiles/conv_traffic.json: mean dram read+write bytes of the launches in the committed ncu --set full capture",
+                "algorithmic_flops_per_launch_mean": conv_flops / max(int(cn.value), 1), "peak_source": peaks["which"],
                 "launches_timed": int(cn.value), "launches_dropped": int(cdrop.value), "kernel_ms_per_step": conv_ms / args.steps,
                 "share_of_step": conv_ms / ms_total if ms_total > 0 else None,
                 "flops_counted": "algorithmic 2*M*N*K of the convolutions (182.4 GFLOP per scene-step at 256x256); "

@@ -65,6 +65,27 @@ def interpolated_poses(old_pose, new_pose, old_az_idx, new_az_idx, n_steps=4, po
     return out
 
 
+def shard_scenes(n_scenes: int, world_size: int, rank: int):
+    """Contiguous block of scene indices owned by `rank` (scenes are independent, so rollouts
+    shard with no data-path collective).  Returns (first, count); blocks differ by at most one scene."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank {rank} / world size {world_size}")
+    base, extra = divmod(n_scenes, world_size)
+    count = base + (1 if rank < extra else 0)
+    first = rank * base + min(rank, extra)
+    return first, count
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """Multi-GPU timings are the max over ranks (one all-reduce of a scalar; the only collective of a rollout)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 class RolloutEngine:
     def __init__(self, scenes, nbp, device, S=256, H=256, W=456, max_steps=100, gathering_factor=0.05,
                  sensor_range=70.0, grid_range=(-40.0, 40.0), n_pieces=4, seed=9):
