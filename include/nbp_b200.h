@@ -133,7 +133,12 @@ typedef struct nbp_conv_desc {
                                               precise, the lo plane starts lo0 elements after src0 */
     const void* src1; int c1; int ld1; int lo1;  /* optional second source, concatenated after src0 along channels */
     int n, h, w;                           /* images and spatial size (stride 1, same-size output) */
-    int taps;                              /* 1 = 1x1 conv, 9 = 3x3 conv with zero padding 1 */
+    int taps;                              /* 1 = 1x1 conv, 9 = 3x3 conv with zero padding 1, 4 = see up2x */
+    int up2x;                              /* 1: the op is nn.Upsample(2, nearest) followed by a 3x3 conv (up_conv, nbp_model.py:23-34)
+                                              computed WITHOUT materialising the upsampled tensor: output pixel (2y+py, 2x+px) is a 2x2
+                                              conv of the source with parity-specific pre-summed weights.  n,h,w are the SOURCE dims, dst
+                                              is [n][2h][2w]; weight holds 4 blocks (parity = py*2+px), each [c_out][4 taps][c_in] packed
+                                              like a normal weight; tap t reads source (y + t/2 - 1 + py, x + t%2 - 1 + px). 2.25x fewer MACs. */
     const void* weight;                    /* fp16 [c_out][taps][c0+c1] (K-major); tap = ky*3+kx.  precise: per tile of
                                               BN = 128|64|32 output channels (largest dividing c_out) BN hi rows then BN lo rows */
     int c_out;                             /* multiple of 32 */

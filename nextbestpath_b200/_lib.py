@@ -38,7 +38,7 @@ class ConvDesc(C.Structure):
     """struct nbp_conv_desc (include/nbp_b200.h)."""
     _fields_ = [("precise", _i), ("src0", _p), ("c0", _i), ("ld0", _i), ("lo0", _i),
                 ("src1", _p), ("c1", _i), ("ld1", _i), ("lo1", _i),
-                ("n", _i), ("h", _i), ("w", _i), ("taps", _i), ("weight", _p), ("c_out", _i),
+                ("n", _i), ("h", _i), ("w", _i), ("taps", _i), ("up2x", _i), ("weight", _p), ("c_out", _i),
                 ("scale", _p), ("shift", _p), ("relu", _i), ("dst", _p), ("dst_ld", _i), ("dst_c_off", _i),
                 ("dst_lo_off", _i)]
 

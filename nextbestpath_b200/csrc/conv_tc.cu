@@ -52,6 +52,8 @@ struct ConvKParams {
     int m_tiles, n_tiles;
     int taps, kc0, kc1;
     int lo0, lo1;                       // element offset of the lo plane inside the tensor maps (PRECISE)
+    int up2x;                           // 1: fused nearest-2x upsample + 3x3 conv as 4 parity-specific 2x2 convs (taps == 4)
+    int b_rows_per_parity;              // rows of the weight matrix per parity block (up2x)
     const float* scale; const float* shift;
     int relu;
     __half* dst; int dst_ld, dst_c_off, dst_lo_off;
@@ -109,7 +111,8 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    const int num_tiles = p.m_tiles * p.n_tiles;
+    const int tiles_per_parity = p.m_tiles * p.n_tiles;
+    const int num_tiles = (p.up2x ? 4 : 1) * tiles_per_parity;
     const int kc_total = p.kc0 + p.kc1;
     const int num_k = p.taps * kc_total;
 
@@ -118,15 +121,19 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int n_tile = tile % p.n_tiles;
-                int mt = tile / p.n_tiles;
+                const int parity = tile / tiles_per_parity;              // 0 unless up2x: (py, px) = (parity >> 1, parity & 1)
+                const int tpl = tile - parity * tiles_per_parity;
+                const int n_tile = tpl % p.n_tiles;
+                int mt = tpl / p.n_tiles;
                 const int tx = mt % p.tiles_x; mt /= p.tiles_x;
                 const int ty = mt % p.tiles_y;
                 const int tb = mt / p.tiles_y;
                 const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tb * p.tn;
+                const int b_row0 = parity * p.b_rows_per_parity + n_tile * Cfg::B_ROWS;
                 for (int tap = 0; tap < p.taps; ++tap) {
-                    const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
-                    const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+                    int dy = 0, dx = 0;
+                    if (p.up2x) { dy = (tap >> 1) - 1 + (parity >> 1); dx = (tap & 1) - 1 + (parity & 1); }
+                    else if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
                     for (int kc = 0; kc < kc_total; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -136,7 +143,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                         uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
                         tma_load_4d(sa, tm, &full_bar[stage], c, x0 + dx, y0 + dy, n0);
                         if (PRECISE) tma_load_4d(sa + A_STAGE_BYTES, tm, &full_bar[stage], c + (first ? p.lo0 : p.lo1), x0 + dx, y0 + dy, n0);
-                        tma_load_2d(smem_b + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], (tap * kc_total + kc) * BLOCK_K, n_tile * Cfg::B_ROWS);
+                        tma_load_2d(smem_b + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], (tap * kc_total + kc) * BLOCK_K, b_row0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -182,14 +189,19 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         const int et = threadIdx.x - 128;                       // 0..127
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int n_tile = tile % p.n_tiles;
-            int mt = tile / p.n_tiles;
+            const int parity = tile / tiles_per_parity;
+            const int tpl = tile - parity * tiles_per_parity;
+            const int n_tile = tpl % p.n_tiles;
+            int mt = tpl / p.n_tiles;
             const int tx = mt % p.tiles_x; mt /= p.tiles_x;
             const int ty = mt % p.tiles_y;
             const int tb = mt / p.tiles_y;
             const int wi = m % p.tw, hi = (m / p.tw) % p.th, ni = m / (p.tw * p.th);
             const int x = tx * p.tw + wi, y = ty * p.th + hi, nn = tb * p.tn + ni;
             const bool valid = x < p.w && y < p.h && nn < p.n;
+            // destination pixel: identity, or (2y+py, 2x+px) of the 2h x 2w image for the fused upsample
+            const int oh = p.up2x ? 2 * p.h : p.h, ow = p.up2x ? 2 * p.w : p.w;
+            const int oy = p.up2x ? 2 * y + (parity >> 1) : y, ox = p.up2x ? 2 * x + (parity & 1) : x;
 
             // stage this tile's affine into smem (buffer `acc`: the previous user of this buffer finished
             // two tiles ago, and the named barrier below orders the writes before the reads)
@@ -203,7 +215,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS);
-            __half* orow = p.dst + ((size_t)((size_t)nn * p.h + y) * p.w + x) * p.dst_ld + p.dst_c_off + n_tile * BLOCK_N;
+            __half* orow = p.dst + ((size_t)((size_t)nn * oh + oy) * ow + ox) * p.dst_ld + p.dst_c_off + n_tile * BLOCK_N;
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; ++c) {
                 uint32_t v[32];
@@ -327,7 +339,7 @@ static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
         if (rc) return rc;
         attr_set = true;
     }
-    const int tiles = kp.m_tiles * kp.n_tiles;
+    const int tiles = kp.m_tiles * kp.n_tiles * (kp.up2x ? 4 : 1);
     const int grid = tiles < sms ? tiles : sms;
     const bool prof = g_prof.enabled && g_prof.used + 2 <= g_prof.ev.size();
     if (g_prof.enabled && !prof) ++g_prof.dropped;
@@ -336,7 +348,9 @@ static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
     if (prof) {
         cudaEventRecord(g_prof.ev[g_prof.used + 1], st);
         g_prof.used += 2;
-        g_prof.flops += 2.0 * (double)kp.n * kp.h * kp.w * (double)(kp.n_tiles * BLOCK_N) * (double)(kp.taps * (kp.kc0 + kp.kc1) * BLOCK_K);
+        // algorithmic flops of the reference op: a fused upsample+3x3 counts as the 3x3 conv on the 2h x 2w image
+        const double pix = (double)kp.n * kp.h * kp.w * (kp.up2x ? 4.0 : 1.0), ktaps = kp.up2x ? 9.0 : (double)kp.taps;
+        g_prof.flops += 2.0 * pix * (double)(kp.n_tiles * BLOCK_N) * ktaps * (double)((kp.kc0 + kp.kc1) * BLOCK_K);
     }
     count_launch();
     return check_cuda(cudaGetLastError(), "conv_gemm_f16 launch");
@@ -349,7 +363,8 @@ using namespace nbp;
 extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     if (!d) return invalid("nbp_conv_fwd: null descriptor");
     if (!d->src0 || !d->weight || !d->scale || !d->shift || !d->dst) return invalid("nbp_conv_fwd: null pointer in descriptor");
-    if (d->taps != 1 && d->taps != 9) return invalid("nbp_conv_fwd: taps must be 1 or 9 (got %d)", d->taps);
+    if (d->taps != 1 && d->taps != 9 && !(d->taps == 4 && d->up2x)) return invalid("nbp_conv_fwd: taps must be 1 or 9, or 4 with up2x (got %d)", d->taps);
+    if (d->up2x && d->taps != 4) return invalid("nbp_conv_fwd: up2x needs the 4-tap parity weights");
     if (d->n <= 0 || d->h <= 0 || d->w <= 0) return invalid("nbp_conv_fwd: bad image dims n=%d h=%d w=%d", d->n, d->h, d->w);
     if (d->c0 <= 0 || d->c0 % BLOCK_K || d->c1 < 0 || d->c1 % BLOCK_K || (d->c1 > 0 && !d->src1))
         return invalid("nbp_conv_fwd: source channels must be positive multiples of 64 (c0=%d c1=%d)", d->c0, d->c1);
@@ -376,6 +391,8 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     kp.m_tiles = kp.tiles_x * kp.tiles_y * kp.tiles_n; kp.n_tiles = d->c_out / block_n;
     kp.taps = d->taps; kp.kc0 = d->c0 / BLOCK_K; kp.kc1 = d->c1 / BLOCK_K;
     kp.lo0 = d->lo0; kp.lo1 = d->lo1;
+    kp.up2x = d->up2x ? 1 : 0;
+    kp.b_rows_per_parity = (precise ? 2 : 1) * d->c_out;
     kp.scale = d->scale; kp.shift = d->shift; kp.relu = d->relu;
     kp.dst = (__half*)d->dst; kp.dst_ld = d->dst_ld; kp.dst_c_off = d->dst_c_off; kp.dst_lo_off = d->dst_lo_off;
     if (kp.tn > 256 || kp.th > 256) return invalid("nbp_conv_fwd: image too small for a 128-pixel tile (w=%d h=%d)", d->w, d->h);
@@ -388,7 +405,7 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     if (rc) return rc;
     // weights: fast [c_out][K]; precise [(c_out/block_n) tiles][W_hi rows ; W_lo rows][K]
     const int planes = precise ? 2 : 1;
-    rc = make_weight_map(&b, d->weight, d->taps * (d->c0 + d->c1), planes * d->c_out, planes * block_n);
+    rc = make_weight_map(&b, d->weight, d->taps * (d->c0 + d->c1), (d->up2x ? 4 : 1) * planes * d->c_out, planes * block_n);
     if (rc) return rc;
 
     static int sms = 0;

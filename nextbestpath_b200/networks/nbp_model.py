@@ -146,6 +146,27 @@ def pack_state_dict(sd, precise=True):
         pk[name] = {"w": _pack_gemm_weight(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1), precise), "scale": s, "shift": b,
                     "c_out": w.shape[0]}
 
+    _ROWS = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}       # parity -> kernel rows/cols summed into 2x2 tap 0 / tap 1
+
+    def up3(name, conv, bn):
+        """nn.Upsample(2, nearest) + 3x3 conv == four parity-specific 2x2 convs on the source (up2x mode of nbp_conv_fwd):
+        output (2y+py, 2x+px) reads source rows y-1+py+ty with the kernel rows that land on them pre-summed."""
+        s, b = _affine(sd, conv, bn)
+        w = sd[conv + ".weight"]                                  # (Cout, Cin, 3, 3)
+        blocks = []
+        for py in (0, 1):
+            for px in (0, 1):
+                taps = []
+                for ty in (0, 1):
+                    for tx in (0, 1):
+                        acc = 0
+                        for ky in _ROWS[py][ty]:
+                            for kx in _ROWS[px][tx]:
+                                acc = acc + w[:, :, ky, kx]
+                        taps.append(acc)                          # (Cout, Cin)
+                blocks.append(_pack_gemm_weight(torch.stack(taps, dim=1).reshape(w.shape[0], -1), precise))
+        pk[name] = {"w": torch.cat(blocks, dim=0).contiguous(), "scale": s, "shift": b, "c_out": w.shape[0]}
+
     w0 = sd["Conv1.conv.0.weight"]
     s, b = _affine(sd, "Conv1.conv.0", "Conv1.conv.1")
     pk["stem"] = {"w": w0.permute(2, 3, 1, 0).reshape(-1, w0.shape[0]).contiguous(), "scale": s, "shift": b, "c_in": w0.shape[1]}
@@ -156,7 +177,7 @@ def pack_state_dict(sd, precise=True):
     for dec in (1, 2):
         for lvl in _DEC_LEVELS[dec]:
             t = f"{lvl}_{dec}"
-            conv3(f"Up{t}", f"Up{t}.up.1", f"Up{t}.up.2")
+            up3(f"Up{t}", f"Up{t}.up.1", f"Up{t}.up.2")
             conv3(f"Up_conv{t}.a", f"Up_conv{t}.conv.0", f"Up_conv{t}.conv.1")
             conv3(f"Up_conv{t}.b", f"Up_conv{t}.conv.3", f"Up_conv{t}.conv.4")
             # attention: one 1x1 GEMM over concat(g, x) with the two BN scales folded into the weights
@@ -197,11 +218,11 @@ class _Act:
         return _Act(self.t, c, self.ld, self.lo, self.h, self.w, self.off + off)
 
 
-def _conv(pk, layer, B, src0, taps, dst, relu=True, src1=None):
+def _conv(pk, layer, B, src0, taps, dst, relu=True, src1=None, up2x=False):
     d = _lib.ConvDesc(1 if pk["precise"] else 0, src0.ptr, src0.c, src0.ld, src0.lo,
                       src1.ptr if src1 is not None else None, src1.c if src1 is not None else 0,
                       src1.ld if src1 is not None else 0, src1.lo if src1 is not None else 0,
-                      B, src0.h, src0.w, taps, layer["w"].data_ptr(), layer["c_out"],
+                      B, src0.h, src0.w, taps, 1 if up2x else 0, layer["w"].data_ptr(), layer["c_out"],
                       layer["scale"].data_ptr(), layer["shift"].data_ptr(), 1 if relu else 0,
                       dst.t.data_ptr(), dst.ld, dst.off, dst.lo)
     _lib.check(_lib.lib().nbp_conv_fwd(ctypes.byref(d), _stream()), "nbp_conv_fwd")
@@ -247,12 +268,9 @@ def _forward_eval(pk, x):
         t = f"{lvl}_{dec}"
         skip = skips[lvl - 1]
         f_l = skip.c
-        up = new(skip.h, skip.w, d.c)
-        _lib.check(L.nbp_upsample2x(d.ptr, B, d.h, d.w, d.c, d.ld, d.lo, up.ptr, up.ld, up.lo, st), "nbp_upsample2x")
         cat = new(skip.h, skip.w, 2 * f_l)               # channels [skip*psi | up-conv output]
         g = cat.channels(f_l, f_l)
-        _conv(pk, pk[f"Up{t}"], B, up, 9, g)
-        del up
+        _conv(pk, pk[f"Up{t}"], B, d, 4, g, up2x=True)   # upsample fused: d is read at its own (half) resolution
         att = pk[f"Att{t}"]
         arelu = new(skip.h, skip.w, att["c_out"])
         _conv(pk, att, B, g, 1, arelu, relu=True, src1=skip)

@@ -65,7 +65,7 @@ def _run_conv(x0, w, scale, shift, relu, taps, precise, x1=None, extra=0, dst_of
     out = torch.full((n, h, wd, planes * ctot), 7.0, dtype=torch.float16, device=DEV)
     sc, sh = scale.to(DEV).contiguous(), shift.to(DEV).contiguous()
     d = _lib.ConvDesc(int(precise), a0.data_ptr(), c0, ld0, lo0, a1.data_ptr() if a1 is not None else None, c1, ld1, lo1,
-                      n, h, wd, taps, wp.data_ptr(), cout, sc.data_ptr(), sh.data_ptr(), int(relu),
+                      n, h, wd, taps, 0, wp.data_ptr(), cout, sc.data_ptr(), sh.data_ptr(), int(relu),
                       out.data_ptr(), planes * ctot, dst_off, ctot if precise else 0)
     _lib.check(_lib.lib().nbp_conv_fwd(ctypes.byref(d), _st()), "nbp_conv_fwd")
     torch.cuda.synchronize()
@@ -121,6 +121,44 @@ def test_conv_fwd_matches_fp64_reference(n, h, w, c0, c1, cout, taps, precise):
         assert (blk[..., :32] == 7.0).all() and (blk[..., 32 + cout:] == 7.0).all()
     got = out[..., 32:32 + cout].float() + (out[..., ctot + 32:ctot + 32 + cout].float() / 2048.0 if precise else 0.0)
     assert (got - r).abs().max().item() <= tol * max(1.0, r.abs().max().item())
+
+
+@pytest.mark.parametrize("precise", [True, False])
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 8, 8, 128, 64), (1, 16, 16, 64, 128), (3, 4, 12, 256, 32)])
+def test_fused_upsample_conv_matches_reference(n, h, w, cin, cout, precise):
+    """up2x mode == F.conv2d(F.interpolate(x, 2, nearest), w, padding=1) (up_conv, nbp_model.py:23-34)."""
+    from nextbestpath_b200.networks.nbp_model import pack_state_dict
+    g = torch.Generator().manual_seed(n + h + cin + cout)
+    q = (lambda t: t) if precise else (lambda t: t.to(torch.float16).float())
+    x = q(torch.randn(n, cin, h, w, generator=g))
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    bias, gamma, beta = torch.randn(cout, generator=g) * 0.1, torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    rm, rv = torch.randn(cout, generator=g) * 0.1, torch.rand(cout, generator=g) + 0.5
+    # reuse the model packer on a fake one-layer state dict via its inner helpers
+    from nextbestpath_b200.networks import nbp_model as M
+    sd = {"c.weight": wt, "c.bias": bias, "b.weight": gamma, "b.bias": beta, "b.running_mean": rm, "b.running_var": rv}
+    scale, shift = M._affine(sd, "c", "b")
+    rows = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+    blocks = []
+    for py in (0, 1):
+        for px in (0, 1):
+            taps = [sum(wt[:, :, ky, kx] for ky in rows[py][ty] for kx in rows[px][tx]) for ty in (0, 1) for tx in (0, 1)]
+            blocks.append(M._pack_gemm_weight(torch.stack(taps, dim=1).reshape(cout, -1), precise))
+    wp = torch.cat(blocks, 0).contiguous().to(DEV)
+    a0, c0, ld0, lo0 = _to_act(x, precise)
+    planes = 2 if precise else 1
+    out = torch.full((n, 2 * h, 2 * w, planes * cout), 7.0, dtype=torch.float16, device=DEV)
+    sc, sh = scale.to(DEV).contiguous(), shift.to(DEV).contiguous()
+    d = _lib.ConvDesc(int(precise), a0.data_ptr(), c0, ld0, lo0, None, 0, 0, 0, n, h, w, 4, 1, wp.data_ptr(), cout,
+                      sc.data_ptr(), sh.data_ptr(), 1, out.data_ptr(), planes * cout, 0, cout if precise else 0)
+    _lib.check(_lib.lib().nbp_conv_fwd(ctypes.byref(d), _st()), "nbp_conv_fwd(up2x)")
+    torch.cuda.synchronize()
+    up = F.interpolate(x.double(), scale_factor=2, mode="nearest")
+    ref = F.relu(F.batch_norm(F.conv2d(up, wt.double(), bias.double(), padding=1), rm.double(), rv.double(), gamma.double(), beta.double(),
+                              False, 0.1, 1e-5)).permute(0, 2, 3, 1).float()
+    got = _from_act(out.cpu(), cout, cout if precise else 0)
+    tol = 2e-5 if precise else 3e-3          # fast mode: the pre-summed weights are rounded to fp16 after summation
+    assert (got - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
 
 
 @pytest.mark.parametrize("precise", [True, False])
