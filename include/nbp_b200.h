@@ -146,6 +146,7 @@ typedef struct nbp_conv_desc {
     int relu;
     void* dst; int dst_ld; int dst_c_off;  /* NHWC fp16 output, written at channels [dst_c_off, dst_c_off+c_out) */
     int dst_lo_off;                        /* precise: lo plane written dst_lo_off elements after the hi channels */
+    int out_f32;                           /* 1: dst is plain fp32 NHWC [pix][dst_ld] (used for dgrad: gradients are fp32) */
 } nbp_conv_desc;
 
 /* tcgen05/TMEM/TMA implicit-GEMM convolution: conv_block / up_conv / Attention_block W_g,W_x (nbp_model.py:8-62) */
@@ -159,9 +160,10 @@ int nbp_conv_fwd(const nbp_conv_desc* desc, void* stream);
 int nbp_conv_profile_begin(int max_launches);
 int nbp_conv_profile_end(double* total_ms_host, double* total_flops_host, uint64_t* launches_host, uint64_t* dropped_host);
 /* Conv1.conv.0: x fp32 NCHW [n,c_in,h,w] counts -> NHWC fp16; weight fp32 [9*c_in][c_out]
- * (tap-major, then input channel), c_out = 64; fused affine + ReLU (nbp_model.py:11-13) */
+ * (tap-major, then input channel), c_out = 64; fused affine + optional ReLU (nbp_model.py:11-13).  Train mode calls it
+ * with scale 1 / shift bias / relu 0 to get the raw pre-BatchNorm tensor. */
 int nbp_conv_first(const float* x, int n, int c_in, int h, int w, const float* weight, const float* scale,
-                   const float* shift, int c_out, void* dst, int dst_ld, int dst_lo, void* stream);
+                   const float* shift, int c_out, int relu, void* dst, int dst_ld, int dst_lo, void* stream);
 /* nn.MaxPool2d(2,2) (nbp_model.py:68) and nn.Upsample(scale_factor=2) nearest (:27) on NHWC fp16 */
 int nbp_maxpool2x2(const void* src, int n, int h, int w, int c, int ld_src, int lo_src, void* dst, int ld_dst, int lo_dst, void* stream);
 int nbp_upsample2x(const void* src, int n, int h, int w, int c, int ld_src, int lo_src, void* dst, int ld_dst, int lo_dst, void* stream);
@@ -174,6 +176,63 @@ int nbp_att_gate(const void* a, int f_int, int ld_a, int lo_a, const void* x, in
  * weight fp32 [c_out][c_in], c_out in {1, 8} */
 int nbp_conv1x1_head(const void* src, int c_in, int ld_src, int lo_src, const float* weight, const float* bias, int c_out,
                      int sigmoid, float* dst, int n, int64_t hw, void* stream);
+
+/* ------------------------------------------------------------------------------------------ a11 (train mode), a13
+ * Train-mode BatchNorm2d (batch statistics, running-stat update: momentum 0.1, unbiased running variance, eps 1e-5 --
+ * torch.nn.BatchNorm2d as instantiated at nbp_model.py:12,15,28,41,46,51) and the backward pass of NBP.forward
+ * (autograd through nbp_model.py:110-160, driven by next_best_path/utility/nbp_utils.py:378-390).
+ * Forward activations: NHWC fp16x2 split tensors (ld, lo as above).  Gradients between layers: plain NHWC fp32.
+ * `workspace` arguments are caller-owned fp64 scratch of the stated length; they are zeroed by the call. */
+int nbp_bn_train_stats(const void* z, int ld, int lo, int64_t npix, int C, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, float momentum, float eps,
+                       float* mean, float* invstd, float* scale, float* shift, double* workspace /* [2C] */, void* stream);
+/* y = act(z*scale + shift) */
+int nbp_affine_act(const void* z, int ld_z, int lo_z, int64_t npix, int C, const float* scale, const float* shift, int relu,
+                   void* y, int ld_y, int lo_y, void* stream);
+/* a = relu(BN_g(zg) + BN_x(zx)) with the two normalisations given as (scale, shift) (nbp_model.py:57-59) */
+int nbp_att_pre(const void* zg, const void* zx, int ld, int lo, int64_t npix, int C, const float* sg, const float* tg,
+                const float* sx, const float* tx, void* a, int ld_a, int lo_a, void* stream);
+/* zpsi = conv1x1(a) (1 channel) and its train-mode BatchNorm2d(1): stat4 = {mean, invstd, scale, shift} on the device */
+int nbp_psi_train(const void* a, int ld_a, int lo_a, int64_t npix, int C, const float* w_psi, const float* b_psi,
+                  const float* gamma1, const float* beta1, float* running_mean1, float* running_var1, float momentum, float eps,
+                  float* zpsi, float* stat4, double* workspace /* [2] */, void* stream);
+/* psi = sigmoid(zpsi*scale+shift); dst[:, c_off:c_off+C] = x * psi; psi_out [npix] saved for backward */
+int nbp_att_apply(const float* zpsi, const float* psi_scale, const float* psi_shift, const void* x, int ld_x, int lo_x, int64_t npix, int C,
+                  void* dst, int ld_d, int c_off, int lo_d, float* psi_out, void* stream);
+/* BatchNorm(+ReLU) backward: dz (fp32 NHWC, row stride ld_dz), dgamma += , dbeta += ; *amax = max|dz| (for operand scaling) */
+int nbp_bn_bwd(const float* dy, int ld_dy, const void* z, int ld_z, int lo_z, int64_t npix, int C, const float* scale, const float* shift,
+               const float* mean, const float* invstd, const float* gamma, int relu, float* dz, int ld_dz, float* amax,
+               float* dgamma, float* dbeta, double* workspace /* [2C] */, void* stream);
+/* fp32 NHWC gradient -> fp16x2 split NHWC scaled by 2^k (amax*2^k in [128,256)); inv_scale_vec[0..n_vec) = 2^-k */
+int nbp_to_split_nhwc(const float* src, int ld_s, int64_t npix, int C, const float* amax, void* dst, int ld_d, int lo_d,
+                      float* inv_scale_vec, int n_vec, void* stream);
+/* fp32 NHWC (scaled like above) or split NHWC (unscaled) -> channel-major split [2][C][n*h][w_pad] for nbp_conv_wgrad;
+ * rows padded from w to w_pad pixels; dst[.., x] = src[.., x + dx] (x-shifted copy; entries without a source are not
+ * written: the caller pre-zeroes dst when w_pad != w or dx != 0); plane_stride = C*row_stride */
+int nbp_to_split_cnhw(const float* src_f32, const void* src_split, int ld_s, int lo_s, int64_t npix, int w, int w_pad, int dx, int C, const float* amax,
+                      void* dst, int64_t row_stride, int64_t plane_stride, float* inv_scale_out, void* stream);
+/* tcgen05 weight-gradient GEMM: dweight[c_out][taps][c_in] += inv_scale * sum_pixels dz[p][co] * x[p+tap][ci].
+ * dz and x are NHWC fp16x2 split tensors (dz from nbp_to_split_nhwc, x the saved forward activation); channel counts
+ * multiples of 64 (pad with zero channels).  Consumed as MN-major UMMA operands straight from the NHWC layout. */
+int nbp_conv_wgrad(const void* dz, int c_out, int ld_dz, int lo_dz, const void* x, int c_in, int ld_x, int lo_x,
+                   int n, int h, int w, int taps, const float* inv_scale, float* dweight, void* stream);
+/* debugging aid: zero-copy host ints [0..3] = {wait tag, block, thread, parity} written when a pipeline wait of the wgrad
+ * kernel times out (the kernel then traps instead of hanging) */
+int nbp_debug_attach_wgrad(int* device_visible_host_ptr);
+int nbp_maxpool2x2_bwd(const float* dy, const void* x, int ld_x, int lo_x, int n, int h, int w, int C, float* dx, int accumulate, void* stream);
+int nbp_upsample2x_bwd(const float* dy, int n, int h, int w, int C, float* dx, int accumulate, void* stream);
+/* Attention_block backward from d(x*psi) to d(x) (+=), d(relu(g1+x1)) = dpre, and the psi conv / BN parameter grads (+=) */
+int nbp_att_bwd(const float* dout, int ld_do, const void* x, int ld_x, int lo_x, const float* psi, const float* zpsi, int64_t npix, int C_l,
+                const float* stat4, const float* gamma1, const void* a, int ld_a, int lo_a, int C_int, const float* w_psi,
+                float* dx_skip, int accumulate, float* dpre, float* dt, float* dw_psi, float* dgamma1, float* dbeta1,
+                double* workspace /* [2 + C_int] */, void* stream);
+/* Final1 / Final2 backward: dsrc fp32 NHWC [pix][c_in]; dweight, dbias += ; out_sigmoid != NULL applies s(1-s) */
+int nbp_head_bwd(const float* dout, const float* out_sigmoid, const void* src, int c_in, int ld_s, int lo_s, const float* weight, int c_out,
+                 int n, int64_t hw, float* dsrc, float* dweight, float* dbias, double* workspace /* [c_out*c_in + c_out] */, void* stream);
+/* Conv1.conv.0 weight gradient: dweight[9*c_in][64] += sum_p x[p+tap][ci] * dz[p][co] (x fp32 NCHW, dz fp32 NHWC) */
+int nbp_stem_wgrad(const float* x, int n, int c_in, int h, int w, const float* dz, float* dweight, double* workspace /* [9*c_in*64] */, void* stream);
+/* y[p][c] += x[p*ld_x + c] */
+int nbp_add_f32(float* y, const float* x, int ld_x, int64_t npix, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,6 +18,8 @@ SOURCES = {
     "scatter.cu": ["-fmad=false"],
     "conv_tc.cu": [],
     "nn_kernels.cu": [],
+    "train_kernels.cu": [],
+    "wgrad_tc.cu": [],
 }
 
 

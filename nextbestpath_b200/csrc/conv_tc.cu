@@ -52,6 +52,7 @@ struct ConvKParams {
     int m_tiles, n_tiles;
     int taps, kc0, kc1;
     int lo0, lo1;                       // element offset of the lo plane inside the tensor maps (PRECISE)
+    int out_f32;                        // 1: the destination is plain fp32 NHWC (gradients), no fp16 planes
     int up2x;                           // 1: fused nearest-2x upsample + 3x3 conv as 4 parity-specific 2x2 convs (taps == 4)
     int b_rows_per_parity;              // rows of the weight matrix per parity block (up2x)
     const float* scale; const float* shift;
@@ -229,6 +230,21 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                 } else {
                     tmem_ld_wait();
                 }
+                if (p.out_f32) {                     // dgrad: fp32 NHWC destination
+                    if (valid) {
+                        float* of = reinterpret_cast<float*>(p.dst) + ((size_t)((size_t)nn * oh + oy) * ow + ox) * p.dst_ld + p.dst_c_off + n_tile * BLOCK_N + c * 32;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 o4;
+                            o4.x = fmaf(__uint_as_float(v[4 * j + 0]), sa[c * 32 + 4 * j + 0], sa[BLOCK_N + c * 32 + 4 * j + 0]);
+                            o4.y = fmaf(__uint_as_float(v[4 * j + 1]), sa[c * 32 + 4 * j + 1], sa[BLOCK_N + c * 32 + 4 * j + 1]);
+                            o4.z = fmaf(__uint_as_float(v[4 * j + 2]), sa[c * 32 + 4 * j + 2], sa[BLOCK_N + c * 32 + 4 * j + 2]);
+                            o4.w = fmaf(__uint_as_float(v[4 * j + 3]), sa[c * 32 + 4 * j + 3], sa[BLOCK_N + c * 32 + 4 * j + 3]);
+                            reinterpret_cast<float4*>(of)[j] = o4;
+                        }
+                    }
+                    continue;
+                }
                 uint32_t packed[16], packed_lo[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -370,12 +386,13 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
         return invalid("nbp_conv_fwd: source channels must be positive multiples of 64 (c0=%d c1=%d)", d->c0, d->c1);
     const bool precise = d->precise != 0;
     const int span0 = precise ? d->lo0 + d->c0 : d->c0, span1 = precise ? d->lo1 + d->c1 : d->c1;
-    if (precise && (d->lo0 < d->c0 || d->lo0 % 8 || (d->c1 > 0 && (d->lo1 < d->c1 || d->lo1 % 8)) || d->dst_lo_off < d->c_out || d->dst_lo_off % 8))
+    if (precise && (d->lo0 < d->c0 || d->lo0 % 8 || (d->c1 > 0 && (d->lo1 < d->c1 || d->lo1 % 8)) ||
+                    (!d->out_f32 && (d->dst_lo_off < d->c_out || d->dst_lo_off % 8))))
         return invalid("nbp_conv_fwd: lo-plane offsets must be >= the channel count and multiples of 8");
     if (d->ld0 < span0 || d->ld0 % 8 || (d->c1 > 0 && (d->ld1 < span1 || d->ld1 % 8)))
         return invalid("nbp_conv_fwd: source pixel strides must cover the planes and be multiples of 8");
     if (d->c_out <= 0 || d->c_out % 32) return invalid("nbp_conv_fwd: c_out must be a positive multiple of 32 (got %d)", d->c_out);
-    if (d->dst_ld % 8 || d->dst_c_off % 8 || d->dst_c_off + (precise ? d->dst_lo_off : 0) + d->c_out > d->dst_ld)
+    if (d->dst_ld % 8 || d->dst_c_off % 8 || d->dst_c_off + ((precise && !d->out_f32) ? d->dst_lo_off : 0) + d->c_out > d->dst_ld)
         return invalid("nbp_conv_fwd: bad destination channel layout ld=%d off=%d lo_off=%d c_out=%d", d->dst_ld, d->dst_c_off, d->dst_lo_off, d->c_out);
     if (((uintptr_t)d->src0 | (uintptr_t)d->src1 | (uintptr_t)d->weight | (uintptr_t)d->dst) & 15)
         return invalid("nbp_conv_fwd: pointers must be 16-byte aligned");
@@ -392,6 +409,7 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     kp.taps = d->taps; kp.kc0 = d->c0 / BLOCK_K; kp.kc1 = d->c1 / BLOCK_K;
     kp.lo0 = d->lo0; kp.lo1 = d->lo1;
     kp.up2x = d->up2x ? 1 : 0;
+    kp.out_f32 = d->out_f32 ? 1 : 0;
     kp.b_rows_per_parity = (precise ? 2 : 1) * d->c_out;
     kp.scale = d->scale; kp.shift = d->shift; kp.relu = d->relu;
     kp.dst = (__half*)d->dst; kp.dst_ld = d->dst_ld; kp.dst_c_off = d->dst_c_off; kp.dst_lo_off = d->dst_lo_off;

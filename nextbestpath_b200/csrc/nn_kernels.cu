@@ -53,7 +53,7 @@ template <int COUT>
 __global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict__ x, int n, int cin, int h, int w,
                                                          const float* __restrict__ wt,      // [9*cin][COUT]
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
-                                                         __half* __restrict__ dst, int dst_ld, int dst_lo) {
+                                                         __half* __restrict__ dst, int dst_ld, int dst_lo, int relu) {
     extern __shared__ float s_w[];                    // 9*cin*COUT weights, then scale, shift
     const int nw = 9 * cin * COUT;
     for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = wt[i];
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict
         for (int c8 = 0; c8 < COUT / 8; ++c8) {
             float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(acc[8 * c8 + j], s_sc[8 * c8 + j], s_sh[8 * c8 + j]), 0.0f);
+            for (int j = 0; j < 8; ++j) { f[j] = fmaf(acc[8 * c8 + j], s_sc[8 * c8 + j], s_sh[8 * c8 + j]); if (relu) f[j] = fmaxf(f[j], 0.0f); }
             store8(o + 8 * c8, dst_lo, f);
         }
     }
@@ -230,7 +230,7 @@ static int check_plane(const char* who, int c, int ld, int lo) {
 }
 
 extern "C" int nbp_conv_first(const float* x, int n, int c_in, int h, int w, const float* weight, const float* scale,
-                              const float* shift, int c_out, void* dst, int dst_ld, int dst_lo, void* stream) {
+                              const float* shift, int c_out, int relu, void* dst, int dst_ld, int dst_lo, void* stream) {
     if (!x || !weight || !scale || !shift || !dst) return invalid("nbp_conv_first: null pointer argument");
     if (n <= 0 || h <= 0 || w <= 0 || c_in <= 0 || c_in > 16) return invalid("nbp_conv_first: bad sizes n=%d c_in=%d h=%d w=%d", n, c_in, h, w);
     if (c_out != 64) return invalid("nbp_conv_first: c_out must be 64 (got %d)", c_out);
@@ -239,7 +239,7 @@ extern "C" int nbp_conv_first(const float* x, int n, int c_in, int h, int w, con
     if ((uintptr_t)dst & 15) return invalid("nbp_conv_first: dst must be 16-byte aligned");
     const size_t smem = sizeof(float) * (size_t)(9 * c_in * 64 + 128);
     conv_first_kernel<64><<<grid_for((size_t)n * h * w, 128), 128, smem, (cudaStream_t)stream>>>(x, n, c_in, h, w, weight, scale, shift,
-                                                                                                  (__half*)dst, dst_ld, dst_lo);
+                                                                                                  (__half*)dst, dst_ld, dst_lo, relu);
     count_launch();
     return check_cuda(cudaGetLastError(), "nbp_conv_first launch");
 }

@@ -49,12 +49,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a broken pipeline traps (-> CUDA error on the host) instead of hanging the GPU box.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded wait: a broken pipeline traps (-> CUDA error on the host) instead of hanging the GPU box.  When a debug
+// word (zero-copy host memory, nbp_debug_attach) is attached, the waiter records who timed out before trapping.
+static __device__ int* nbp_dbg_ptr = nullptr;
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) {
-            printf("nbp: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+        if (++spins > (1u << 22)) {
+            if (nbp_dbg_ptr) {
+                nbp_dbg_ptr[1] = blockIdx.x; nbp_dbg_ptr[2] = threadIdx.x; nbp_dbg_ptr[3] = (int)parity; nbp_dbg_ptr[0] = tag;
+                __threadfence_system();
+            }
             __trap();
         }
     }
@@ -129,10 +134,25 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// MN-major operand (rows of the shared tile are K, each row holds 64 contiguous M/N elements = 128 bytes, SW128):
+// LBO = byte distance between consecutive 64-element M/N atoms, SBO = byte distance between 8-row K groups.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // Instruction descriptor, kind::f16: fp16 A/B (format 0), fp32 accumulate (c_format 1), both K-major, dense.
 //   [4,6) c_format | [7,10) a_format | [10,13) b_format | 15 a_major | 16 b_major | [17,23) N>>3 | [24,29) M>>4
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
     return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// same with both operands MN-major (a_major = b_major = 1)
+__host__ __device__ constexpr uint32_t umma_idesc_f16_mn(int M, int N) {
+    return umma_idesc_f16(M, N) | (1u << 15) | (1u << 16);
 }
 
 }  // namespace tc

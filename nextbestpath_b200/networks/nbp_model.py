@@ -77,15 +77,19 @@ class NBP(nn.Module):
         if not isinstance(x, torch.Tensor) or not x.is_cuda:
             raise RuntimeError("nextbestpath_b200.NBP runs on CUDA tensors only (no CPU fallback); "
                                "the CPU oracle lives in oracle/nbp_torch.py and is test infrastructure")
-        if self.training or torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and x.requires_grad:
-            if self.training:
-                raise NotImplementedError("train-mode forward/backward of the B200 NBP is not built yet (round 2); "
-                                          "call .eval() for the inference rollout path")
         if x.dim() != 4 or x.shape[1] != self.img_ch:
             raise RuntimeError(f"expected (B,{self.img_ch},S,S) input, got {tuple(x.shape)}")
         if x.shape[2] % 16 or x.shape[3] % 16:
             raise RuntimeError("spatial size must be a multiple of 16 (four 2x2 poolings)")
         x = x.contiguous().float()
+        if self.training:
+            # train mode: batch-statistics BatchNorm + autograd through the CUDA backward kernels (nbp_train.py)
+            from .nbp_train import NBPTrainFunction
+            named = [(n, p) for n, p in self.named_parameters() if n != "log_vars"]
+            for n, p in named:
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError(f"parameter {n} must be a contiguous fp32 CUDA tensor")
+            return NBPTrainFunction.apply(self, x, tuple(n for n, _ in named), *[p for _, p in named])
         outs1, outs2 = [], []
         pk = self._pack(x.device)
         for b0 in range(0, x.shape[0], self.max_chunk):
@@ -251,7 +255,7 @@ def _forward_eval(pk, x):
     a = new(S, S2, 64)
     stem = pk["stem"]
     _lib.check(L.nbp_conv_first(x.data_ptr(), B, stem["c_in"], S, S2, stem["w"].data_ptr(), stem["scale"].data_ptr(),
-                                stem["shift"].data_ptr(), 64, a.ptr, a.ld, a.lo, st), "nbp_conv_first")
+                                stem["shift"].data_ptr(), 64, 1, a.ptr, a.ld, a.lo, st), "nbp_conv_first")
     x1 = new(S, S2, 64)
     _conv(pk, pk["Conv1.b"], B, a, 9, x1)
     del a

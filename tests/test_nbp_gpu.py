@@ -218,7 +218,7 @@ def test_pointwise_kernels_match_torch(precise):
     dst = torch.empty((2, 32, 32, planes * 64), dtype=torch.float16, device=DEV)
     wp = w0.permute(2, 3, 1, 0).reshape(45, 64).contiguous().to(DEV)
     xd, scd, shd = xin.to(DEV), sc.to(DEV), sh.to(DEV)
-    _lib.check(L.nbp_conv_first(xd.data_ptr(), 2, 5, 32, 32, wp.data_ptr(), scd.data_ptr(), shd.data_ptr(), 64, dst.data_ptr(),
+    _lib.check(L.nbp_conv_first(xd.data_ptr(), 2, 5, 32, 32, wp.data_ptr(), scd.data_ptr(), shd.data_ptr(), 64, 1, dst.data_ptr(),
                                 planes * 64, 64 if precise else 0, _st()), "stem")
     ref = F.relu(F.conv2d(xin.double(), w0.double(), padding=1) * sc.double()[None, :, None, None] + sh.double()[None, :, None, None]).permute(0, 2, 3, 1).float()
     assert (_from_act(dst, 64, 64 if precise else 0) - ref).abs().max() <= (3e-6 if precise else 1e-3) * ref.abs().max()

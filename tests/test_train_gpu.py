@@ -1,0 +1,119 @@
+"""GPU parity of the train-mode path (SURVEY.md section 8 rows a11 train mode, a12, a13): forward with batch-statistics
+BatchNorm, NBP.loss, backward through the CUDA kernels (tcgen05 dgrad / wgrad), against (i) the fp32 CPU oracle run with
+torch autograd and (ii) the fixture produced by the reference's own NBP class (tests/golden/nbp_train.npz).
+Tolerance: conv grads within 1e-3 relative fp32 (BASELINE.json north_star) -- per parameter, ||g - g_ref|| / ||g_ref||."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from nextbestpath_b200.networks import NBP
+from oracle import nbp_torch as NT
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _targets(B, S, K=40, seed=5):
+    g2 = torch.Generator().manual_seed(seed)
+    tgt_idx = torch.stack((torch.randint(0, 8, (B, K), generator=g2), torch.randint(0, S // 4, (B, K), generator=g2),
+                           torch.randint(0, S // 4, (B, K), generator=g2)), dim=-1)
+    tgt_val = torch.rand(B, K, generator=g2) * 10
+    layout = (torch.rand(B, 1, S, S, generator=g2) < 0.2).float()
+    return tgt_idx, tgt_val, layout
+
+
+def _loss(loss_fn, p1, p2, tgt_idx, tgt_val, layout):
+    """the sparse gather of nbp_utils.py:373-381 followed by NBP.loss"""
+    B = p1.shape[0]
+    ti = tgt_idx.to(p1.device)
+    pred = torch.stack([p1[b, ti[b, :, 0], ti[b, :, 1], ti[b, :, 2]] for b in range(B)])
+    return loss_fn(pred, tgt_val.to(p1.device), p2, layout.to(p1.device))
+
+
+def _oracle_step(sd, xb, tgt_idx, tgt_val, layout):
+    spec = {k: kind for k, _, kind in NT.state_dict_spec()}
+    params = [k for k in sd if spec[k] in ("param", "conv_w", "conv_b", "bn_w", "bn_b")]
+    for k in params:
+        sd[k].requires_grad_(True)
+    p1, p2 = NT.forward(sd, xb, training=True)
+    loss = _loss(lambda a, b, c, d: NT.loss(sd, a, b, c, d), p1, p2, tgt_idx, tgt_val, layout)
+    loss.backward()
+    return p1.detach(), p2.detach(), loss.detach(), {k: sd[k].grad for k in params}
+
+
+@pytest.mark.parametrize("B,S", [(2, 64), (1, 128)])
+def test_train_step_matches_oracle(B, S):
+    sd = NT.golden_state_dict(seed=9)
+    net = NBP(); net.load_state_dict(sd); net.to(DEV).train()
+    xb = NT.count_like_input(B, S, seed=4)
+    tgt_idx, tgt_val, layout = _targets(B, S)
+    p1, p2 = net(xb.to(DEV))
+    loss = _loss(net.loss, p1, p2, tgt_idx, tgt_val, layout)
+    loss.backward()
+    torch.cuda.synchronize()
+    r1, r2, rloss, rg = _oracle_step(sd, xb, tgt_idx, tgt_val, layout)
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    assert rel(p1.detach().cpu(), r1) <= 1e-3 and rel(p2.detach().cpu(), r2) <= 1e-3
+    assert abs(loss.item() - rloss.item()) <= 1e-4 * abs(rloss.item())
+    # BatchNorm buffers after the step
+    st = net.state_dict()
+    for k in ("Conv1.conv.1", "Conv3.conv.4", "Up4_1.up.2", "Att3_2.W_x.1", "Att2_2.psi.1", "Up_conv2_2.conv.4"):
+        assert rel(st[k + ".running_mean"].cpu(), sd[k + ".running_mean"]) <= 1e-4, k
+        assert rel(st[k + ".running_var"].cpu(), sd[k + ".running_var"]) <= 1e-4, k
+        assert int(st[k + ".num_batches_tracked"]) == 1
+    # gradients: every parameter, relative to the oracle's
+    worst, checked = [], 0
+    scale = max(float(g.norm()) for g in rg.values())
+    for n, p in net.named_parameters():
+        g, gr = p.grad.detach().cpu(), rg[n]
+        if float(gr.norm()) < 1e-6 * scale:                    # conv biases in front of BatchNorm: analytically zero
+            assert float(g.norm()) <= 1e-5 * scale, n
+            continue
+        e = rel(g, gr)
+        worst.append((e, n)); checked += 1
+    worst.sort(reverse=True)
+    print(f"B={B} S={S}: {checked} parameter gradients compared; worst:", [(f"{e:.2e}", n) for e, n in worst[:5]])
+    assert checked > 140
+    assert worst[0][0] <= 1e-3, worst[:5]
+
+
+def test_train_step_matches_reference_fixture(golden_dir):
+    """loss / gradient norms / running stats stored by the reference's own NBP class (make_golden.py)."""
+    g = np.load(os.path.join(golden_dir, "nbp_train.npz"))
+    sd = NT.golden_state_dict(seed=9)
+    net = NBP(); net.load_state_dict(sd); net.to(DEV).train()
+    xb = NT.count_like_input(2, 64, seed=4)
+    layout = torch.from_numpy(np.unpackbits(g["layout"])[: 2 * 64 * 64].reshape(2, 1, 64, 64).astype(np.float32))
+    p1, p2 = net(xb.to(DEV))
+    loss = _loss(net.loss, p1, p2, torch.from_numpy(g["tgt_idx"]), torch.from_numpy(g["tgt_val"]), layout)
+    loss.backward()
+    assert abs(loss.item() - g["loss"][0]) <= 1e-4 * abs(g["loss"][0])
+    assert np.abs(p1.detach().cpu().numpy() - g["out1"]).max() <= 1e-3 * np.abs(g["out1"]).max()
+    names = [str(n) for n in g["grad_names"]]
+    mine = dict(net.named_parameters())
+    gn = np.array([float(mine[n].grad.double().norm()) for n in names])
+    big = g["grad_norms"] > 1e-6 * g["grad_norms"].max()
+    assert np.all(np.abs(gn[big] - g["grad_norms"][big]) <= 2e-3 * g["grad_norms"][big])
+    pr = mine["Conv5.conv.3.weight"].grad.reshape(-1)[:16].cpu().numpy()
+    assert np.abs(pr - g["probe_Conv5_conv_3_weight"]).max() <= 2e-3 * np.abs(g["probe_Conv5_conv_3_weight"]).max() + 1e-9
+    assert np.abs(net.state_dict()["Conv1.conv.1.running_mean"].cpu().numpy() - g["rm_conv1"]).max() < 1e-4
+
+
+def test_adamw_steps_reduce_loss():
+    """The reference's optimiser loop (nbp_utils.py:228,383-390) drives the module unchanged."""
+    torch.manual_seed(0)
+    net = NBP(); net.load_state_dict(NT.golden_state_dict(seed=9)); net.to(DEV).train()
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    xb = NT.count_like_input(2, 64, seed=4).to(DEV)
+    tgt_idx, tgt_val, layout = _targets(2, 64)
+    losses = []
+    for _ in range(6):
+        opt.zero_grad()
+        p1, p2 = net(xb)
+        loss = _loss(net.loss, p1, p2, tgt_idx, tgt_val, layout)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
