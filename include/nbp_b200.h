@@ -147,6 +147,10 @@ typedef struct nbp_conv_desc {
     void* dst; int dst_ld; int dst_c_off;  /* NHWC fp16 output, written at channels [dst_c_off, dst_c_off+c_out) */
     int dst_lo_off;                        /* precise: lo plane written dst_lo_off elements after the hi channels */
     int out_f32;                           /* 1: dst is plain fp32 NHWC [pix][dst_ld] (used for dgrad: gradients are fp32) */
+    int k_chunk;                           /* precise mode: number of 64-element K slices summed inside the tensor core's (truncating)
+                                              fp32 accumulator before the partial sum is folded into fp32 round-to-nearest registers;
+                                              0 = default (8).  Smaller = more accurate, slower (measured: 8 -> 3.6e-5 network error,
+                                              2 -> floor of the 22-bit operands, -10 % throughput) */
 } nbp_conv_desc;
 
 /* tcgen05/TMEM/TMA implicit-GEMM convolution: conv_block / up_conv / Attention_block W_g,W_x (nbp_model.py:8-62) */
@@ -213,9 +217,11 @@ int nbp_to_split_cnhw(const float* src_f32, const void* src_split, int ld_s, int
                       void* dst, int64_t row_stride, int64_t plane_stride, float* inv_scale_out, void* stream);
 /* tcgen05 weight-gradient GEMM: dweight[c_out][taps][c_in] += inv_scale * sum_pixels dz[p][co] * x[p+tap][ci].
  * dz and x are NHWC fp16x2 split tensors (dz from nbp_to_split_nhwc, x the saved forward activation); channel counts
- * multiples of 64 (pad with zero channels).  Consumed as MN-major UMMA operands straight from the NHWC layout. */
+ * multiples of 64 (pad with zero channels).  Consumed as MN-major UMMA operands straight from the NHWC layout.
+ * max_k_tiles > 0 bounds the number of 64-pixel slices accumulated inside the tensor core per partial result (the
+ * partials are combined with fp32 atomics); 0 = only as many splits as needed to fill the GPU. */
 int nbp_conv_wgrad(const void* dz, int c_out, int ld_dz, int lo_dz, const void* x, int c_in, int ld_x, int lo_x,
-                   int n, int h, int w, int taps, const float* inv_scale, float* dweight, void* stream);
+                   int n, int h, int w, int taps, const float* inv_scale, float* dweight, int max_k_tiles, void* stream);
 /* debugging aid: zero-copy host ints [0..3] = {wait tag, block, thread, parity} written when a pipeline wait of the wgrad
  * kernel times out (the kernel then traps instead of hanging) */
 int nbp_debug_attach_wgrad(int* device_visible_host_ptr);

@@ -40,7 +40,7 @@ class ConvDesc(C.Structure):
                 ("src1", _p), ("c1", _i), ("ld1", _i), ("lo1", _i),
                 ("n", _i), ("h", _i), ("w", _i), ("taps", _i), ("up2x", _i), ("weight", _p), ("c_out", _i),
                 ("scale", _p), ("shift", _p), ("relu", _i), ("dst", _p), ("dst_ld", _i), ("dst_c_off", _i),
-                ("dst_lo_off", _i), ("out_f32", _i)]
+                ("dst_lo_off", _i), ("out_f32", _i), ("k_chunk", _i)]
 
 
 SIGNATURES.update({
@@ -64,7 +64,7 @@ SIGNATURES.update({
     "nbp_bn_bwd": (_i, [_p, _i, _p, _i, _i, _l, _i, _p, _p, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p]),
     "nbp_to_split_nhwc": (_i, [_p, _i, _l, _i, _p, _p, _i, _i, _p, _i, _p]),
     "nbp_to_split_cnhw": (_i, [_p, _p, _i, _i, _l, _i, _i, _i, _i, _p, _p, _l, _l, _p, _p]),
-    "nbp_conv_wgrad": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "nbp_conv_wgrad": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
     "nbp_maxpool2x2_bwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
     "nbp_upsample2x_bwd": (_i, [_p, _i, _i, _i, _i, _p, _i, _p]),
     "nbp_att_bwd": (_i, [_p, _i, _p, _i, _i, _p, _p, _l, _i, _p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),

@@ -30,6 +30,7 @@
 //               so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "nbp_common.cuh"
@@ -53,6 +54,8 @@ struct ConvKParams {
     int taps, kc0, kc1;
     int lo0, lo1;                       // element offset of the lo plane inside the tensor maps (PRECISE)
     int out_f32;                        // 1: the destination is plain fp32 NHWC (gradients), no fp16 planes
+    int kchunk;                         // K stages accumulated inside TMEM before the partial sum is folded into fp32
+                                        // registers (round-to-nearest); the tensor core's own accumulator truncates
     int up2x;                           // 1: fused nearest-2x upsample + 3x3 conv as 4 parity-specific 2x2 convs (taps == 4)
     int b_rows_per_parity;              // rows of the weight matrix per parity block (up2x)
     const float* scale; const float* shift;
@@ -158,10 +161,12 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+              for (int ks0 = 0; ks0 < num_k; ks0 += p.kchunk) {
+                const int ks1 = min(num_k, ks0 + p.kchunk);
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS);
-                for (int ks = 0; ks < num_k; ++ks) {
+                for (int ks = ks0; ks < ks1; ++ks) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES));
@@ -169,7 +174,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; ++k) {
                         // +32 bytes (16 fp16) along K inside the 128-byte swizzle row: +2 in the encoded address
-                        umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_main, (ks | k) != 0 ? 1u : 0u);
+                        umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_main, (ks > ks0 || k > 0) ? 1u : 0u);
                         if (PRECISE) {
                             // A_lo * W_hi accumulates into the acc_lo columns that the UMMA above just wrote (in-order pipe)
                             const uint64_t alo = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES + A_STAGE_BYTES));
@@ -179,8 +184,9 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                     umma_commit(&empty_bar[stage]);           // frees the smem slot once these MMAs have read it
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);                  // accumulator complete -> epilogue
+                umma_commit(&tfull_bar[acc]);                  // (partial) accumulator complete -> epilogue
                 acc ^= 1; if (acc == 0) acc_phase ^= 1;
+              }
             }
         }
     } else if (warp >= 4) {
@@ -189,6 +195,8 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         const int m = q * 32 + lane;                            // accumulator row = pixel of the tile
         const int et = threadIdx.x - 128;                       // 0..127
         int acc = 0; uint32_t acc_phase = 0;
+        int tsel = 0;
+        const int n_chunks = (num_k + p.kchunk - 1) / p.kchunk;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int parity = tile / tiles_per_parity;
             const int tpl = tile - parity * tiles_per_parity;
@@ -204,53 +212,42 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             const int oh = p.up2x ? 2 * p.h : p.h, ow = p.up2x ? 2 * p.w : p.w;
             const int oy = p.up2x ? 2 * y + (parity >> 1) : y, ox = p.up2x ? 2 * x + (parity & 1) : x;
 
-            // stage this tile's affine into smem (buffer `acc`: the previous user of this buffer finished
+            // stage this tile's affine into smem (two buffers alternate per tile: the previous user of a buffer finished
             // two tiles ago, and the named barrier below orders the writes before the reads)
-            float* sa = s_affine + acc * 2 * BLOCK_N;
+            float* sa = s_affine + tsel * 2 * BLOCK_N;
+            tsel ^= 1;
             for (int i = et; i < BLOCK_N; i += 128) {
                 sa[i] = p.scale[n_tile * BLOCK_N + i];
                 sa[BLOCK_N + i] = p.shift[n_tile * BLOCK_N + i];
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
 
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS);
-            __half* orow = p.dst + ((size_t)((size_t)nn * oh + oy) * ow + ox) * p.dst_ld + p.dst_c_off + n_tile * BLOCK_N;
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
-                if (PRECISE) {
-                    uint32_t vl[32];
-                    tmem_ld_32x32(t_row + (uint32_t)(BLOCK_N + c * 32), vl);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(vl[j]), 1.0f / 2048.0f, __uint_as_float(v[j])));
-                } else {
-                    tmem_ld_wait();
-                }
+            const size_t opix = (size_t)((size_t)nn * oh + oy) * ow + ox;
+            __half* orow = p.dst + opix * p.dst_ld + p.dst_c_off + n_tile * BLOCK_N;
+            float* orow_f = reinterpret_cast<float*>(p.dst) + opix * p.dst_ld + p.dst_c_off + n_tile * BLOCK_N;
+
+            // affine + activation + store of 32 consecutive output channels held as fp32 in v[]
+            auto finish = [&](int c, const float* v) {
                 if (p.out_f32) {                     // dgrad: fp32 NHWC destination
                     if (valid) {
-                        float* of = reinterpret_cast<float*>(p.dst) + ((size_t)((size_t)nn * oh + oy) * ow + ox) * p.dst_ld + p.dst_c_off + n_tile * BLOCK_N + c * 32;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float4 o4;
-                            o4.x = fmaf(__uint_as_float(v[4 * j + 0]), sa[c * 32 + 4 * j + 0], sa[BLOCK_N + c * 32 + 4 * j + 0]);
-                            o4.y = fmaf(__uint_as_float(v[4 * j + 1]), sa[c * 32 + 4 * j + 1], sa[BLOCK_N + c * 32 + 4 * j + 1]);
-                            o4.z = fmaf(__uint_as_float(v[4 * j + 2]), sa[c * 32 + 4 * j + 2], sa[BLOCK_N + c * 32 + 4 * j + 2]);
-                            o4.w = fmaf(__uint_as_float(v[4 * j + 3]), sa[c * 32 + 4 * j + 3], sa[BLOCK_N + c * 32 + 4 * j + 3]);
-                            reinterpret_cast<float4*>(of)[j] = o4;
+                            o4.x = fmaf(v[4 * j + 0], sa[c * 32 + 4 * j + 0], sa[BLOCK_N + c * 32 + 4 * j + 0]);
+                            o4.y = fmaf(v[4 * j + 1], sa[c * 32 + 4 * j + 1], sa[BLOCK_N + c * 32 + 4 * j + 1]);
+                            o4.z = fmaf(v[4 * j + 2], sa[c * 32 + 4 * j + 2], sa[BLOCK_N + c * 32 + 4 * j + 2]);
+                            o4.w = fmaf(v[4 * j + 3], sa[c * 32 + 4 * j + 3], sa[BLOCK_N + c * 32 + 4 * j + 3]);
+                            reinterpret_cast<float4*>(orow_f + c * 32)[j] = o4;
                         }
                     }
-                    continue;
+                    return;
                 }
                 uint32_t packed[16], packed_lo[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int col = c * 32 + 2 * j;
-                    float a0 = fmaf(__uint_as_float(v[2 * j]), sa[col], sa[BLOCK_N + col]);
-                    float a1 = fmaf(__uint_as_float(v[2 * j + 1]), sa[col + 1], sa[BLOCK_N + col + 1]);
+                    float a0 = fmaf(v[2 * j], sa[col], sa[BLOCK_N + col]);
+                    float a1 = fmaf(v[2 * j + 1], sa[col + 1], sa[BLOCK_N + col + 1]);
                     if (p.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); }
                     a0 = fminf(fmaxf(a0, -65504.0f), 65504.0f);
                     a1 = fminf(fmaxf(a1, -65504.0f), 65504.0f);
@@ -272,11 +269,63 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                         for (int j = 0; j < 4; ++j) ol[j] = make_uint4(packed_lo[4 * j], packed_lo[4 * j + 1], packed_lo[4 * j + 2], packed_lo[4 * j + 3]);
                     }
                 }
+            };
+            // one 32-column group of the current TMEM buffer as fp32 (acc_hi + acc_lo/2048 in the fp16x2 mode)
+            auto load_group = [&](uint32_t t_row, int c, float* out) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
+                if (PRECISE) {
+                    uint32_t vl[32];
+                    tmem_ld_32x32(t_row + (uint32_t)(BLOCK_N + c * 32), vl);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) out[j] = fmaf(__uint_as_float(vl[j]), 1.0f / 2048.0f, __uint_as_float(v[j]));
+                } else {
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) out[j] = __uint_as_float(v[j]);
+                }
+            };
+            auto release = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                acc ^= 1; if (acc == 0) acc_phase ^= 1;
+            };
+
+            if (n_chunks == 1) {
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS);
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    float v[32];
+                    load_group(t_row, c, v);
+                    finish(c, v);
+                }
+                release();
+            } else {
+                // long reductions: every K chunk is summed inside TMEM (truncating accumulator), the chunks are summed here
+                // in fp32 round-to-nearest -- error grows with sqrt(chunks) instead of linearly with K
+                float racc[BLOCK_N];
+#pragma unroll
+                for (int j = 0; j < BLOCK_N; ++j) racc[j] = 0.0f;
+                for (int ch = 0; ch < n_chunks; ++ch) {
+                    mbar_wait(&tfull_bar[acc], acc_phase);
+                    tc_fence_after();
+                    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS);
+#pragma unroll
+                    for (int c = 0; c < BLOCK_N / 32; ++c) {
+                        float v[32];
+                        load_group(t_row, c, v);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) racc[c * 32 + j] += v[j];
+                    }
+                    release();
+                }
+#pragma unroll
+                for (int c = 0; c < BLOCK_N / 32; ++c) finish(c, &racc[c * 32]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            acc ^= 1; if (acc == 0) acc_phase ^= 1;
         }
     }
 
@@ -410,6 +459,15 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     kp.lo0 = d->lo0; kp.lo1 = d->lo1;
     kp.up2x = d->up2x ? 1 : 0;
     kp.out_f32 = d->out_f32 ? 1 : 0;
+    {   // K stages (64 elements each) per in-TMEM accumulation chain; env NBP_CONV_KCHUNK overrides (0 = unbounded)
+        static int kchunk_env = -1;
+        if (kchunk_env < 0) { const char* e = getenv("NBP_CONV_KCHUNK"); kchunk_env = e ? atoi(e) : 8; }
+        const int total = d->taps * (kp.kc0 + kp.kc1);
+        const int want = d->k_chunk > 0 ? d->k_chunk : kchunk_env;
+        kp.kchunk = (want <= 0 || !precise) ? total : want;
+        if (kp.kchunk > total) kp.kchunk = total;
+        if (kp.kchunk < 1) kp.kchunk = 1;
+    }
     kp.b_rows_per_parity = (precise ? 2 : 1) * d->c_out;
     kp.scale = d->scale; kp.shift = d->shift; kp.relu = d->relu;
     kp.dst = (__half*)d->dst; kp.dst_ld = d->dst_ld; kp.dst_c_off = d->dst_c_off; kp.dst_lo_off = d->dst_lo_off;

@@ -247,7 +247,7 @@ static int wg_pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p
 static int wg_pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
 
 extern "C" int nbp_conv_wgrad(const void* dz, int c_out, int ld_dz, int lo_dz, const void* x, int c_in, int ld_x, int lo_x,
-                              int n, int h, int w, int taps, const float* inv_scale, float* dweight, void* stream) {
+                              int n, int h, int w, int taps, const float* inv_scale, float* dweight, int max_k_tiles, void* stream) {
     if (!dz || !x || !dweight) return invalid("nbp_conv_wgrad: null pointer argument");
     if (taps != 1 && taps != 9) return invalid("nbp_conv_wgrad: taps must be 1 or 9");
     if (c_out <= 0 || c_in <= 0 || c_out % 64 || c_in % 64) return invalid("nbp_conv_wgrad: channel counts must be positive multiples of 64 (pad with zeros): c_out=%d c_in=%d", c_out, c_in);
@@ -281,6 +281,10 @@ extern "C" int nbp_conv_wgrad(const void* dz, int c_out, int ld_dz, int lo_dz, c
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     const int out_tiles = p.m_tiles * p.n_tiles * taps;
     int splits = (2 * sms + out_tiles - 1) / out_tiles;
+    // The tensor core's fp32 accumulator truncates (error grows linearly with the chain length); weight gradients are
+    // sums with heavy cancellation, so the in-TMEM chain is bounded to max_k_tiles 64-pixel slices and the partial
+    // results are combined by fp32 round-to-nearest atomics.
+    if (max_k_tiles > 0 && (p.k_tiles + splits - 1) / splits > max_k_tiles) splits = (p.k_tiles + max_k_tiles - 1) / max_k_tiles;
     if (splits > p.k_tiles) splits = p.k_tiles;
     if (splits < 1) splits = 1;
     p.splits = splits;

@@ -222,13 +222,13 @@ class _Act:
         return _Act(self.t, c, self.ld, self.lo, self.h, self.w, self.off + off)
 
 
-def _conv(pk, layer, B, src0, taps, dst, relu=True, src1=None, up2x=False):
+def _conv(pk, layer, B, src0, taps, dst, relu=True, src1=None, up2x=False, k_chunk=0):
     d = _lib.ConvDesc(1 if pk["precise"] else 0, src0.ptr, src0.c, src0.ld, src0.lo,
                       src1.ptr if src1 is not None else None, src1.c if src1 is not None else 0,
                       src1.ld if src1 is not None else 0, src1.lo if src1 is not None else 0,
                       B, src0.h, src0.w, taps, 1 if up2x else 0, layer["w"].data_ptr(), layer["c_out"],
                       layer["scale"].data_ptr(), layer["shift"].data_ptr(), 1 if relu else 0,
-                      dst.t.data_ptr(), dst.ld, dst.off, dst.lo)
+                      dst.t.data_ptr(), dst.ld, dst.off, dst.lo, 0, k_chunk)
     _lib.check(_lib.lib().nbp_conv_fwd(ctypes.byref(d), _stream()), "nbp_conv_fwd")
 
 

@@ -23,6 +23,8 @@ from . import nbp_model as M
 
 _DEC_LEVELS = M._DEC_LEVELS
 BN_MOMENTUM, BN_EPS = 0.1, 1e-5
+TRAIN_K_CHUNK = 2            # training keeps the forward / dgrad accumulation chains short: gradients are ill-conditioned
+WGRAD_MAX_K_TILES = int(__import__("os").environ.get("NBP_WGRAD_MAX_K_TILES", "4"))     # 64-pixel slices per in-TMEM chain
 
 
 def _st():
@@ -73,7 +75,7 @@ def _raw_conv(t, w2d, bias, src, taps, dst):
     """dst = conv(src) + bias (no normalisation): the raw pre-BatchNorm tensor z."""
     pk = {"precise": True}
     layer = {"w": M._pack_gemm_weight(w2d, True), "scale": torch.ones_like(bias), "shift": bias.contiguous(), "c_out": w2d.shape[0]}
-    M._conv(pk, layer, t.B, src, taps, dst, relu=False)
+    M._conv(pk, layer, t.B, src, taps, dst, relu=False, k_chunk=TRAIN_K_CHUNK)
     return layer
 
 
@@ -115,7 +117,7 @@ def _conv_backward(t, name, w, src, dz, amax, taps, need_dsrc=True):
     # ---- weight gradient: tcgen05 GEMM over the pixel dimension, operands read in place (MN-major)
     dW = t.zeros(kpad, taps, cin)
     _chk(t.L.nbp_conv_wgrad(dzs.ptr, kpad, dzs.ld, dzs.lo, src.ptr, cin, src.ld, src.lo, B, h, wd, taps, inv_vec.data_ptr(),
-                            dW.data_ptr(), _st()), "nbp_conv_wgrad")
+                            dW.data_ptr(), WGRAD_MAX_K_TILES, _st()), "nbp_conv_wgrad")
     k = 3 if taps == 9 else 1
     t.pgrad(name + ".weight", w).add_(dW[:cout].view(cout, k, k, cin).permute(0, 3, 1, 2))
     t.pgrad(name + ".bias", w[:, 0, 0, 0])          # exactly zero in front of a train-mode BatchNorm; heads handle theirs
@@ -129,7 +131,7 @@ def _conv_backward(t, name, w, src, dz, amax, taps, need_dsrc=True):
     dsrc = t.f32(npix, cin)
     layer = {"w": M._pack_gemm_weight(wd2, True), "scale": inv_vec, "shift": t.zeros(cin), "c_out": cin}
     d = _lib.ConvDesc(1, dzs.ptr, kpad, dzs.ld, dzs.lo, None, 0, 0, 0, B, h, wd, taps, 0, layer["w"].data_ptr(), cin,
-                      layer["scale"].data_ptr(), layer["shift"].data_ptr(), 0, dsrc.data_ptr(), cin, 0, 0, 1)
+                      layer["scale"].data_ptr(), layer["shift"].data_ptr(), 0, dsrc.data_ptr(), cin, 0, 0, 1, TRAIN_K_CHUNK)
     _chk(t.L.nbp_conv_fwd(ctypes.byref(d), _st()), "nbp_conv_fwd(dgrad)")
     return dsrc
 

@@ -22,6 +22,8 @@ CASES = [
     (2, 16, 16, 64, 32, 1),       # attention 1x1, BLOCK_N = 32, dgrad K padded 32 -> 64
     (1, 64, 64, 64, 64, 9),       # one K slice = one image row
     (2, 8, 16, 128, 256, 1),
+    (2, 128, 128, 64, 64, 9),     # long pixel reduction (32768 pixels)
+    (1, 128, 128, 128, 64, 9),
 ]
 
 
@@ -56,3 +58,37 @@ def test_conv_backward_kernels(n, h, w, cin, cout, taps):
     e_x = rel(dsrc.view(n, h, w, cin).permute(0, 3, 1, 2).cpu(), xd.grad)
     print(f"n={n} h={h} w={w} cin={cin} cout={cout} taps={taps}: wgrad rel {e_w:.2e}, dgrad rel {e_x:.2e}")
     assert e_w <= 2e-5 and e_x <= 2e-5
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 64), (2, 128, 128, 64, 64), (1, 32, 32, 128, 256)])
+def test_conv_bn_relu_block_forward_backward(n, h, w, cin, cout):
+    """One conv_block half (3x3 conv + train-mode BatchNorm + ReLU, nbp_model.py:11-13) forward and backward against
+    fp64 torch autograd: output, running statistics, d(input), d(weight), d(gamma), d(beta)."""
+    g = torch.Generator().manual_seed(n + h + cin + cout)
+    x = torch.relu(torch.randn(n, cin, h, w, generator=g)) * 2.0
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    gamma, beta = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    rm, rv = torch.zeros(cout), torch.ones(cout)
+    dy = torch.randn(n, cout, h, w, generator=g) * 1e-4
+    # fp64 reference
+    xd = x.double().requires_grad_(True)
+    P = [t.double().requires_grad_(True) for t in (wt, b, gamma, beta)]
+    rmd, rvd = rm.double().clone(), rv.double().clone()
+    yref = F.relu(F.batch_norm(F.conv2d(xd, P[0], P[1], padding=1), rmd, rvd, P[2], P[3], True, 0.1, 1e-5))
+    yref.backward(dy.double())
+    # ours
+    tape = T._Tape(torch.device(DEV), n)
+    sd = {"c.weight": wt.to(DEV), "c.bias": b.to(DEV), "b.weight": gamma.to(DEV), "b.bias": beta.to(DEV),
+          "b.running_mean": rm.to(DEV), "b.running_var": rv.to(DEV), "b.num_batches_tracked": torch.zeros((), dtype=torch.long, device=DEV)}
+    src = _act_split(x)
+    y, bw = T._cbr(tape, sd, "c", "b", src)
+    dsrc = bw(dy.permute(0, 2, 3, 1).reshape(-1, cout).contiguous().to(DEV))
+    torch.cuda.synchronize()
+    rel = lambda a, bb: float((a.double() - bb).norm() / bb.norm())
+    yv = (y.t[..., :cout].float() + y.t[..., cout:].float() / 2048.0).cpu().permute(0, 3, 1, 2)
+    errs = {"y": rel(yv, yref.detach()), "running_mean": rel(sd["b.running_mean"].cpu(), rmd), "running_var": rel(sd["b.running_var"].cpu(), rvd),
+            "dx": rel(dsrc.view(n, h, w, cin).permute(0, 3, 1, 2).cpu(), xd.grad), "dW": rel(tape.pgrads["c.weight"].cpu(), P[0].grad),
+            "dgamma": rel(tape.pgrads["b.weight"].cpu(), P[2].grad), "dbeta": rel(tape.pgrads["b.bias"].cpu(), P[3].grad)}
+    print(f"n={n} h={h} w={w} cin={cin} cout={cout}: " + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()))
+    assert all(v <= 1e-4 for v in errs.values()), errs
