@@ -204,7 +204,7 @@ def run_ours(args):
     B_total = args.scenes
     per = [shard_scenes(B_total, world, r)[1] for r in range(world)]
     first, B = shard_scenes(B_total, world, rank)
-    n_total = args.prefill + 2 * (args.warmup + args.steps) + 2
+    n_total = args.prefill + 2 * (args.warmup + args.steps) + 3
     scenes, poses, az = make_workload(B, args.level, n_total + 8, rank0_scene_index=first)
     sd = NT.golden_state_dict(seed=9)
     net = NBP(); net.load_state_dict(sd); net.to(dev).eval()
@@ -254,6 +254,16 @@ def run_ours(args):
     ms_per_step = ms_total / args.steps
     value = B_total * args.steps / (ms_total / 1e3)
 
+    # ================= per-stage device time of one extra step (diagnostic, outside both timed regions)
+    from nextbestpath_b200.rollout import STAGE_NAMES
+    eng.stage_events = []
+    eng.step(eng.upload_move(poses[:, t], poses[:, t + 1], az[:, t], az[:, t + 1]))
+    torch.cuda.synchronize()
+    evs = eng.stage_events
+    eng.stage_events = None
+    stage_ms = {nm: evs[i].elapsed_time(evs[i + 1]) for i, nm in enumerate(STAGE_NAMES)}
+    t += 1
+
     # ================= e2e: host-driven steps (host pose interpolation, pinned H2D, D2H of the maps)
     h_val = torch.empty((B, S // 4, S // 4), dtype=torch.float32).pin_memory()
     h_map8 = torch.empty((B, 8, S // 4, S // 4), dtype=torch.float32).pin_memory()
@@ -297,8 +307,10 @@ def run_ours(args):
                 "algorithmic_flops_per_launch_mean": conv_flops / max(int(cn.value), 1), "peak_source": peaks["which"],
                 "launches_timed": int(cn.value), "launches_dropped": int(cdrop.value), "kernel_ms_per_step": conv_ms / args.steps,
                 "share_of_step": conv_ms / ms_total if ms_total > 0 else None,
-                "flops_counted": "algorithmic 2*M*N*K of the convolutions (182.4 GFLOP per scene-step at 256x256); "
-                                 + ("precision fp16x2 executes 3 tensor-core passes per algorithmic flop, so frac <= 1/3 by construction"
+                "flops_counted": "algorithmic 2*M*N*K of the reference's convolutions (182.4 GFLOP per scene-step at 256x256; the fused "
+                                 "upsample+conv layers are counted as the 3x3 conv on the upsampled image they replace); "
+                                 + ("precision fp16x2 executes 3 tensor-core passes per executed flop, and the fused up-sampling "
+                                    "executes 2.25x fewer MACs on 6 layers: executed tensor flops = 2.47 x algorithmic"
                                     if args.precision == "fp16x2" else "precision fp16: 1 pass"),
                 "mma_passes": 3 if args.precision == "fp16x2" else 1}
 
@@ -334,6 +346,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
+            "stage_ms": stage_ms,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -160,9 +160,9 @@ __global__ void __launch_bounds__(BP_THREADS) bp_write(BpParams p) {
     const int scene = p.frame_scene[f];
     if (threadIdx.x < 9) sR[threadIdx.x] = p.R[f * 9 + threadIdx.x];
     if (threadIdx.x < 3) sT[threadIdx.x] = p.T[f * 3 + threadIdx.x];
-    __syncthreads();
     if (threadIdx.x == 0 && sel.final_len >= 0) p.cloud_len[scene] = sel.final_len;   // bp_offsets already read the old value
-    if (sel.k == 0) return;
+    if (sel.k == 0) return;                                                            // block-uniform
+    // (sR / sT become visible at the __syncthreads() below, before their first use)
 
     const float* z = p.zbuf + (size_t)f * p.HW;
     const uint8_t* m = p.mask ? p.mask + (size_t)f * p.HW : nullptr;
@@ -170,15 +170,31 @@ __global__ void __launch_bounds__(BP_THREADS) bp_write(BpParams p) {
     const Feistel perm = make_feistel(p.seed, p.frame_uid ? p.frame_uid[f] : f, p.key_bits);
     float* out = p.cloud + (size_t)scene * (size_t)p.cap * 3;
 
+    // every warp owns one contiguous range of pixels (row-major order is preserved): two passes over the range, the
+    // first counts the kept pixels, the second writes them at (frame base + ranges before + rank inside the range).
+    // Only two block-wide barriers per frame.
+    const int warp = threadIdx.x >> 5, lane = lane_id(), nwarp = BP_THREADS / 32;
+    const int per = (((p.HW + nwarp - 1) / nwarp) + 31) & ~31;
+    const int i0 = warp * per, i1 = min(p.HW, i0 + per);
+    int cnt = 0;
+    for (int b = i0; b < i1; b += 32) {
+        const int i = b + lane;
+        const bool keep = i < i1 && pixel_valid(p, z, m, i) && (all || perm((uint32_t)i) <= sel.tau);
+        cnt += __popc(__ballot_sync(0xffffffffu, keep));
+    }
+    if (lane == 0) s_wcnt[warp] = cnt;
+    __syncthreads();
+    int running = sel.base;
+    for (int w = 0; w < warp; ++w) running += s_wcnt[w];
+
     const float wm = p.wm, hm = p.hm, mm1 = p.mm1;
-    int running = sel.base, dropped = 0;
-    for (int c0 = 0; c0 < p.HW; c0 += BP_THREADS) {
-        const int i = c0 + threadIdx.x;
-        bool keep = false;
-        if (i < p.HW && pixel_valid(p, z, m, i)) keep = all || perm((uint32_t)i) <= sel.tau;
-        int tot;
-        const int slot = running + block_compact(keep, s_wcnt, tot);
-        running += tot;
+    int dropped = 0;
+    for (int b = i0; b < i1; b += 32) {
+        const int i = b + lane;
+        const bool keep = i < i1 && pixel_valid(p, z, m, i) && (all || perm((uint32_t)i) <= sel.tau);
+        const unsigned ball = __ballot_sync(0xffffffffu, keep);
+        const int slot = running + __popc(ball & ((1u << lane) - 1u));
+        running += __popc(ball);
         if (keep) {
             if (slot < p.cap) {
                 const int row = i / p.W, col = i - row * p.W;
@@ -186,9 +202,9 @@ __global__ void __launch_bounds__(BP_THREADS) bp_write(BpParams p) {
                 // NDC tables of macarons_utils.py:2270-2279
                 const float nx = fsub(wm, fmul(fdiv((float)col, mm1), 2.0f));
                 const float ny = fsub(hm, fmul(fdiv((float)row, mm1), 2.0f));
-                const float s = fmul(d, p.tan_half);
-                const float dx = fsub(fmul(nx, s), sT[0]);
-                const float dy = fsub(fmul(ny, s), sT[1]);
+                const float sc = fmul(d, p.tan_half);
+                const float dx = fsub(fmul(nx, sc), sT[0]);
+                const float dy = fsub(fmul(ny, sc), sT[1]);
                 const float dz = fsub(d, sT[2]);
                 float* o = out + (size_t)slot * 3;
                 o[0] = fadd(fadd(fmul(dx, sR[0]), fmul(dy, sR[1])), fmul(dz, sR[2]));

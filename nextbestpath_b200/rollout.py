@@ -86,6 +86,9 @@ def max_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
+STAGE_NAMES = ("A_backproject_key", "B_grid_scatter", "C_nbp_forward", "D_render_4_views", "E_backproject_4_frames")
+
+
 class RolloutEngine:
     def __init__(self, scenes, nbp, device, S=256, H=256, W=456, max_steps=100, gathering_factor=0.05,
                  sensor_range=70.0, grid_range=(-40.0, 40.0), n_pieces=4, seed=9):
@@ -129,6 +132,7 @@ class RolloutEngine:
         self.view_scene4_host = list(range(B)) * 4
         self.step_idx = 0
         self.max_points_bound = 0
+        self.stage_events = None        # set to [] to record CUDA events at the stage boundaries of the next step(s)
         self._uid_base = torch.arange(B, dtype=torch.int32, device=dev) * 8
 
     # ------------------------------------------------------------------ helpers
@@ -175,25 +179,32 @@ class RolloutEngine:
         B, H, W = self.B, self.H, self.W
         poses4, R4, T4 = move
         n_new = int(self.gf * H * W)
+        ev = self.stage_events
+        mark = (lambda: ev.append(torch.cuda.Event(enable_timing=True)) or ev[-1].record()) if ev is not None else (lambda: None)
+        mark()
         # ---- A: back-project the current key frame
         ops.backproject_append(self.frames[0], self.frame_R[0], self.frame_T[0], self.scene_ids, self.cloud, self.cloud_len,
                                frame_uid=self._uids(1, 0), fov_range=self.sensor_range, gathering_factor=self.gf,
                                seed=self.seed, overflow=self.overflow)
         self.max_points_bound = min(self.cap, self.max_points_bound + n_new)
+        mark()
         out1 = out2 = vmax = None
         if run_network:
             # ---- B: model input
             ops.grid_scatter(self.cloud, self.cloud_len, self.pose, self.slab_bounds, self.n_bounds, self.S, traj=self.traj,
                              traj_len=self.traj_len, n_pieces=self.n_pieces, grid_range=self.grid_range,
                              max_points=self.max_points_bound, out=self.grid)
+            mark()
             # ---- C: network
             with torch.no_grad():
                 out1, out2 = self.nbp(self.grid)
             vmax = out1.amax(dim=1)
+            mark()
         # ---- D: move + render 4 frames straight into slots 1..4 (slot 4 is the new key frame)
         self._render(R4, T4, self.view_scene4, self.view_scene4_host, self.frames[1:5].view(4 * B, H, W))
         self.frame_R[1:5].copy_(R4.view(4, B, 9)); self.frame_T[1:5].copy_(T4.view(4, B, 3))
         self._append_traj(poses4[:, :, :3].permute(1, 0, 2))
+        mark()
         # ---- E: back-project [old key, interp1, interp2, interp3]; frames of a scene append in slot order
         ops.backproject_append(self.frames[0:4].view(4 * B, H, W), self.frame_R[0:4].view(4 * B, 9), self.frame_T[0:4].view(4 * B, 3),
                                self.view_scene4, self.cloud, self.cloud_len, frame_uid=self._uids(4, 1),
@@ -202,5 +213,6 @@ class RolloutEngine:
         # ---- the new key frame becomes slot 0
         self.frames[0].copy_(self.frames[4]); self.frame_R[0].copy_(self.frame_R[4]); self.frame_T[0].copy_(self.frame_T[4])
         self.pose.copy_(poses4[3])
+        mark()
         self.step_idx += 1
         return StepOutput(out1, out2, vmax, self.grid) if run_network else None
