@@ -240,6 +240,23 @@ int nbp_stem_wgrad(const float* x, int n, int c_in, int h, int w, const float* d
 /* y[p][c] += x[p*ld_x + c] */
 int nbp_add_f32(float* y, const float* x, int ld_x, int64_t npix, int C, void* stream);
 
+/* ------------------------------------------------------------------------------------------ SURVEY section 8(f) row 1
+ * The re-plan branch right after NBP.forward (next_best_path/testers/nbp_planning.py:166-233).
+ * nbp_obstacle_fuse (:168-190): fused = (pred >= threshold); where the cloud has any point (all_cnt > 0) fused = (slice_cnt > 0)
+ * (slice = points within +-0.1 of the camera height); along the trajectory (traj > 0) fused = 0.  full_proj = (all_cnt > 0).
+ * pred/fused/full_proj [n, S, S] fp32; the three count images are [S*S] per scene with the given scene strides (elements), e.g.
+ * channels of nbp_grid_scatter outputs. */
+int nbp_obstacle_fuse(const float* pred, const float* all_cnt, int64_t all_stride, const float* slice_cnt, int64_t slice_stride,
+                      const float* traj, int64_t traj_stride, int n, int S, float threshold, float* fused, float* full_proj, void* stream);
+/* nbp_candidate_scores (:193-231 + check_pixel_values macarons_utils.py:86-100): cand [n, max_cand, 3] world positions, n_cand [n],
+ * skip [n, max_cand] (known collisions, may be NULL), pose [n,5], value_map [n, n_ch, Sv, Sv], full_proj [n, S, S].
+ * Per candidate: cell (value-map row, col; -1 if outside), value = max over channels at that cell, density = full_proj at the
+ * S-grid cell, valid = inside the value map AND some full_proj cell == 1 within +-window px.  The reference's score is
+ * value - 10*density (computed by the caller in double, as the Python loop does). */
+int nbp_candidate_scores(const float* cand, const int32_t* n_cand, int max_cand, const uint8_t* skip, const float* pose,
+                         const float* value_map, int n_ch, int Sv, const float* full_proj, int S, int n,
+                         float range_lo, float range_hi, int window, float* value, float* density, int32_t* cell, uint8_t* valid, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

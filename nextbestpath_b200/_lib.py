@@ -72,6 +72,8 @@ SIGNATURES.update({
     "nbp_stem_wgrad": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "nbp_add_f32": (_i, [_p, _p, _i, _l, _i, _p]),
     "nbp_debug_attach_wgrad": (_i, [_p]),
+    "nbp_obstacle_fuse": (_i, [_p, _p, _l, _p, _l, _p, _l, _i, _i, _f, _p, _p, _p]),
+    "nbp_candidate_scores": (_i, [_p, _p, _i, _p, _p, _p, _i, _i, _p, _i, _i, _f, _f, _i, _p, _p, _p, _p, _p]),
 })
 
 _lib = None

@@ -16,6 +16,7 @@ SOURCES = {
     "raster.cu": ["-fmad=false"],
     "backproject.cu": ["-fmad=false"],
     "scatter.cu": ["-fmad=false"],
+    "planner.cu": ["-fmad=false"],
     "conv_tc.cu": [],
     "nn_kernels.cu": [],
     "train_kernels.cu": [],

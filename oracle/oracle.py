@@ -280,3 +280,53 @@ def build_model_input(cloud, pose, bounds, trajectory, S: int = 256, grid_range=
     traj = np.asarray(trajectory, dtype=np.float32).reshape(-1, 3)
     out[n_pieces] = map_points(transform_points(traj, pose), S, grid_range)
     return out
+
+
+# --------------------------------------------------------------------------- re-plan read-out
+def fuse_obstacle_map(pred_obstacle, cloud, pose, trajectory, S: int = 256, grid_range=(-40, 40), threshold: float = 0.13):
+    """Obstacle-map fusion of the re-plan branch, nbp_planning.py:168-190.
+    pred_obstacle (S,S) probabilities -> (fused (S,S) in {0,1}, full_proj (S,S) in {0,1}).
+    PINNED by tests/golden/planner.npz, produced by executing the reference's own lines (make_golden.py)."""
+    cloud = np.asarray(cloud, dtype=np.float32).reshape(-1, 3)
+    pose = np.asarray(pose, dtype=np.float32).reshape(-1)
+    fused = (np.asarray(pred_obstacle, dtype=np.float32) >= f32(threshold)).astype(np.float32)
+    p2d = transform_points(cloud, pose)
+    full_proj = np.minimum(map_points(p2d, S, grid_range), f32(1))                      # full_pc_projection[... > 1] = 1
+    lo, hi = f32(float(pose[1]) - 0.1), f32(float(pose[1]) + 0.1)                       # python float thresholds, compared in fp32
+    sel = (cloud[:, 1] < hi) & (cloud[:, 1] > lo)
+    slice_img = (map_points(p2d[sel], S, grid_range) > 0).astype(np.float32)
+    seen = full_proj > 0
+    fused[seen] = slice_img[seen]
+    traj_img = map_points(transform_points(trajectory, pose), S, grid_range)
+    fused[traj_img > 0] = 0
+    return fused, full_proj
+
+
+def score_candidates(value_map, full_proj, candidates, pose, skip=None, S: int = 256, Sv: int = 64, grid_range=(-40, 40), window: int = 10):
+    """Candidate scoring loop nbp_planning.py:193-231 + check_pixel_values macarons_utils.py:86-100.
+    value_map (8,Sv,Sv), full_proj (S,S), candidates (M,3).  Returns (valid (M,) bool, cell (M,2) int, score (M,) float64)
+    with score = value - 10*density exactly as the Python loop computes it (float64 of two fp32 .item()s)."""
+    vm = np.asarray(value_map, dtype=np.float32)
+    fp = np.asarray(full_proj, dtype=np.float32)
+    cand = np.asarray(candidates, dtype=np.float32).reshape(-1, 3)
+    M = len(cand)
+    valid = np.zeros(M, dtype=bool); cell = -np.ones((M, 2), dtype=np.int64); score = np.zeros(M, dtype=np.float64)
+    max_gain = vm.max(axis=0)
+    p2d = transform_points(cand, pose)
+    gv = cell_index(p2d, Sv, grid_range)
+    gs = cell_index(p2d, S, grid_range)
+    for j in range(M):
+        if skip is not None and skip[j]:
+            continue
+        r, c = int(gv[j, 0]), int(gv[j, 1])
+        if not (0 <= r < Sv and 0 <= c < Sv):
+            continue
+        cell[j] = (r, c)
+        x, y = int(gs[j, 0]), int(gs[j, 1])
+        dens = fp[x, y]                                                     # numpy wraps negative indices like torch
+        region = fp[max(x - window, 0): min(x + window + 1, S), max(y - window, 0): min(y + window + 1, S)]
+        if not (region == 1).any():
+            continue
+        valid[j] = True
+        score[j] = float(max_gain[r, c]) - 10 * float(dens)
+    return valid, cell, score

@@ -43,6 +43,57 @@ def sparse(a):
     return idx.astype(np.int32), a.reshape(-1)[idx]
 
 
+def _ref_lines(path, start_marker, end_marker, include_end=True):
+    """Source lines of a reference file between two marker substrings (executed from where they lie, never copied)."""
+    import textwrap
+    lines = open(path).read().split("\n")
+    a = next(i for i, l in enumerate(lines) if start_marker in l)
+    b = next(i for i, l in enumerate(lines) if end_marker in l and i >= a)
+    return textwrap.dedent("\n".join(lines[a: b + 1 if include_end else b]))
+
+
+def planner_golden(ru):
+    """planner.npz: the re-plan read-out.  The reference code is inline in compute_nbp_trajectory, so the
+    lines next_best_path/testers/nbp_planning.py:166-233 and macarons_utils.py:86-100 are EXECUTED here from the reference tree
+    (exec of the source text with a prepared namespace), with `nbp` stubbed to return fixed maps."""
+    import ast
+    g = torch.Generator().manual_seed(21)
+    N = 5000
+    pose = torch.tensor([4.0, 1.8, -6.5, 0.0, 90.0])
+    full_pc = torch.empty(N, 3)
+    full_pc[:, 0] = pose[0] + torch.rand(N, generator=g) * 70 - 35
+    full_pc[:, 1] = torch.rand(N, generator=g) * 10 - 1
+    full_pc[:, 2] = pose[2] + torch.rand(N, generator=g) * 70 - 35
+    full_pc[:1500, 0] = torch.round(full_pc[:1500, 0] / 6) * 6                      # walls
+    full_pc[1500:2500, 1] = pose[1] + (torch.rand(1000, generator=g) - 0.5) * 0.3    # many points near the camera-height slice
+    value_map = torch.rand(1, 8, 64, 64, generator=g) * 10
+    obstacle = torch.rand(1, 1, 256, 256, generator=g)
+    traj = pose[:3] + torch.cumsum(torch.randn(30, 3, generator=g) * torch.tensor([1.5, 0.0, 1.5]), 0)
+    ns = {"torch": torch, "ast": ast, "device": "cpu", "pc2img_size": (256, 256), "prediction_range": (-40, 40), "value_map_size": (64, 64),
+          "transform_points_to_n_pieces": ru.transform_points_to_n_pieces, "map_points_to_n_imgs": ru.map_points_to_n_imgs,
+          "get_point_position_in_the_img": ru.get_point_position_in_the_img, "full_pc": full_pc, "camera_current_pose": pose,
+          "nbp": lambda x: (value_map, obstacle.clone()), "Dijkstra_path": [], "path_record": 0}
+    exec(_ref_lines("/root/reference/macarons/utility/macarons_utils.py", "def check_pixel_values", "return contains_one"), ns)
+    ns["current_pc_imgs"] = torch.zeros(1, 4, 256, 256)
+    ns["current_previous_trajectory_img"] = ru.map_points_to_n_imgs(ru.transform_points_to_n_pieces(traj, pose, "cpu"), (256, 256), (-40, 40), "cpu").unsqueeze(0)
+    keys, pts = [], []
+    for i in range(-14, 15):
+        for k in range(-14, 15):
+            keys.append(str([i + 20, 0, k + 20])); pts.append(torch.tensor([pose[0] + 3.0 * i, pose[1], pose[2] + 3.0 * k]))
+    ns["splited_pose_space"] = dict(zip(keys, pts))
+    ns["collision_list"] = [[20, 0, 21], [25, 0, 25], [10, 0, 30]]
+    exec(_ref_lines("/root/reference/next_best_path/testers/nbp_planning.py", "predicted_value_map, predicted_obstacle_map = nbp(",
+                    "camera_position_value_list.sort("), ns)
+    lst = ns["camera_position_value_list"]
+    np.savez_compressed(os.path.join(HERE, "planner.npz"), cloud=full_pc.numpy(), pose=pose.numpy(), value_map=value_map[0].numpy(),
+                        obstacle=obstacle[0, 0].numpy(), traj=traj.numpy(), cand=torch.stack(pts).numpy(), cand_keys=np.array(keys),
+                        collision=np.array(ns["collision_list"]), fused=ns["predicted_obstacle_map"][0, 0].numpy().astype(np.uint8),
+                        full_proj=ns["full_pc_projection"][0, 0].numpy().astype(np.uint8),
+                        out_keys=np.array([e[0] for e in lst]), out_cell=np.array([[int(e[1][0]), int(e[1][1])] for e in lst]),
+                        out_score=np.array([e[2] for e in lst], dtype=np.float64))
+    print("planner golden:", len(lst), "valid candidates of", len(keys), "; fused ones", int(ns["predicted_obstacle_map"].sum()))
+
+
 def main():
     NBP, ru = import_reference()
     from oracle import nbp_torch as O
@@ -118,6 +169,7 @@ def main():
                         rm_conv1=st["Conv1.conv.1.running_mean"].numpy(), rv_conv1=st["Conv1.conv.1.running_var"].numpy(),
                         rm_up22=st["Up_conv2_2.conv.4.running_mean"].numpy(),
                         **{"probe_" + k.replace(".", "_"): v for k, v in probe.items()})
+    planner_golden(ru)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
