@@ -24,7 +24,7 @@ from . import nbp_model as M
 _DEC_LEVELS = M._DEC_LEVELS
 BN_MOMENTUM, BN_EPS = 0.1, 1e-5
 TRAIN_K_CHUNK = 2            # training keeps the forward / dgrad accumulation chains short: gradients are ill-conditioned
-WGRAD_MAX_K_TILES = int(__import__("os").environ.get("NBP_WGRAD_MAX_K_TILES", "4"))     # 64-pixel slices per in-TMEM chain
+WGRAD_MAX_K_TILES = int(__import__("os").environ.get("NBP_WGRAD_MAX_K_TILES", "0"))     # 0: split K only as far as needed to fill the GPU (bounding the in-TMEM chain showed no accuracy benefit, measured)
 
 
 def _st():
