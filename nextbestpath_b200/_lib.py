@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnbp_b200.so")
+LIB_PATH = os.environ.get("NBP_B200_LIB") or os.path.join(_HERE, "libnbp_b200.so")   # env override: A/B kernel experiments only
 
 _p = C.c_void_p
 _i = C.c_int
