@@ -134,6 +134,8 @@ class RolloutEngine:
         self.max_points_bound = 0
         self.stage_events = None        # set to [] to record CUDA events at the stage boundaries of the next step(s)
         self._uid_base = torch.arange(B, dtype=torch.int32, device=dev) * 8
+        self._copy_stream = None        # side stream of the device->host read-back (created on first use)
+        self._copy_done = None
 
     # ------------------------------------------------------------------ helpers
     def _uids(self, n_slots, slot0):
@@ -172,10 +174,19 @@ class RolloutEngine:
         pin = lambda t: t.contiguous().pin_memory().to(self.dev, non_blocking=True)
         return pin(poses), pin(R.reshape(-1, 9)), pin(T)
 
-    def step(self, move, run_network: bool = True):
+    def wait_host_outputs(self):
+        """Block the host until the read-back started by the last ``step(..., host_out=...)`` has landed.  The device
+        keeps running stages D and E of that step meanwhile."""
+        if self._copy_done is not None:
+            self._copy_done.synchronize()
+
+    def step(self, move, run_network: bool = True, host_out=None):
         """One rollout step for all scenes.  ``move`` = (poses (4,B,5), R (4*B,9), T (4*B,3)) on the device
         (from ``upload_move``): the 4 cameras leading to the next key pose.  ``run_network=False`` advances the
-        geometry only (stages A, D, E): used to fast-forward a rollout to a given pose index."""
+        geometry only (stages A, D, E): used to fast-forward a rollout to a given pose index.
+        ``host_out`` = (value_max, value_map, obstacle_map) pinned host tensors: the network outputs are copied to them
+        on a side stream as soon as stage C ends, overlapping the copy with stages D and E (which do not depend on the
+        maps: the move was decided before the step); ``wait_host_outputs()`` tells when they can be read."""
         B, H, W = self.B, self.H, self.W
         poses4, R4, T4 = move
         n_new = int(self.gf * H * W)
@@ -200,6 +211,17 @@ class RolloutEngine:
                 out1, out2 = self.nbp(self.grid)
             vmax = out1.amax(dim=1)
             mark()
+            if host_out is not None:
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(device=self.dev)
+                    self._copy_done = torch.cuda.Event()
+                ready = torch.cuda.Event(); ready.record()
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(ready)
+                    for h, d in zip(host_out, (vmax, out1, out2)):
+                        h.copy_(d, non_blocking=True)
+                        d.record_stream(self._copy_stream)
+                    self._copy_done.record()
         # ---- D: move + render 4 frames straight into slots 1..4 (slot 4 is the new key frame)
         self._render(R4, T4, self.view_scene4, self.view_scene4_host, self.frames[1:5].view(4 * B, H, W))
         self.frame_R[1:5].copy_(R4.view(4, B, 9)); self.frame_T[1:5].copy_(T4.view(4, B, 3))

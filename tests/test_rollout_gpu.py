@@ -115,3 +115,27 @@ def test_rollout_subsampled_statistics():
     n = runs[0][0]
     assert (n > 0).all() and (n <= n_steps * 5 * int(0.05 * H * W)).all()
     assert runs[0][2][:, :4].sum() > 0
+
+
+def test_rollout_host_outputs_overlap_copy():
+    """step(..., host_out=...) reads the maps back on a side stream under stages D/E: the pinned host buffers hold the
+    same bits as the device outputs once wait_host_outputs() returns, and the engine state is unaffected."""
+    B, n_steps = 2, 2
+    scenes = [syn.make_scene(60 + i, tri_budget=700) for i in range(B)]
+    walks = [syn.random_walk(sc, n_steps + 1, seed=90 + i) for i, sc in enumerate(scenes)]
+    poses = np.stack([w[0] for w in walks]); az = np.stack([w[1] for w in walks])
+    net = NBP(); net.load_state_dict(NT.golden_state_dict(seed=9)); net.to(DEV).eval()
+    h = (torch.empty((B, S // 4, S // 4)).pin_memory(), torch.empty((B, 8, S // 4, S // 4)).pin_memory(), torch.empty((B, 1, S, S)).pin_memory())
+    runs = []
+    for use_host in (False, True):
+        eng = RolloutEngine(scenes, net, DEV, S=S, H=H, W=W, max_steps=n_steps + 1, gathering_factor=1.0, sensor_range=30.0)
+        eng.reset(poses[:, 0])
+        for t in range(n_steps):
+            mv = eng.upload_move(poses[:, t], poses[:, t + 1], az[:, t], az[:, t + 1])
+            out = eng.step(mv, host_out=h if use_host else None)
+            if use_host:
+                eng.wait_host_outputs()
+                assert torch.equal(h[0], out.value_max.cpu()) and torch.equal(h[1], out.value_map.cpu()) and torch.equal(h[2], out.obstacle_map.cpu())
+        torch.cuda.synchronize()
+        runs.append((eng.cloud_len.cpu().clone(), out.value_map.cpu().clone()))
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
