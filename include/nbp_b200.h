@@ -207,6 +207,13 @@ int nbp_att_apply(const float* zpsi, const float* psi_scale, const float* psi_sh
 int nbp_bn_bwd(const float* dy, int ld_dy, const void* z, int ld_z, int lo_z, int64_t npix, int C, const float* scale, const float* shift,
                const float* mean, const float* invstd, const float* gamma, int relu, float* dz, int ld_dz, float* amax,
                float* dgamma, float* dbeta, double* workspace /* [2C] */, void* stream);
+/* Same backward, but dz leaves directly as the fp16x2 split GEMM operand of dgrad / wgrad (dz_split, pixel stride ld_s, lo plane at
+ * lo_s), scaled by a power of two chosen from an upper bound of max|dz| that the reduction pass provides (amax2: 2-float scratch);
+ * inv_scale_vec[0..n_vec) = 2^-k.  dz may be NULL then.  Replaces nbp_bn_bwd + nbp_to_split_nhwc (no fp32 dz round trip). */
+int nbp_bn_bwd_split(const float* dy, int ld_dy, const void* z, int ld_z, int lo_z, int64_t npix, int C, const float* scale, const float* shift,
+                     const float* mean, const float* invstd, const float* gamma, int relu, float* dz, int ld_dz, float* amax,
+                     float* dgamma, float* dbeta, double* workspace /* [2C] */, void* dz_split, int ld_s, int lo_s, float* amax2,
+                     float* inv_scale_vec, int n_vec, void* stream);
 /* fp32 NHWC gradient -> fp16x2 split NHWC scaled by 2^k (amax*2^k in [128,256)); inv_scale_vec[0..n_vec) = 2^-k */
 int nbp_to_split_nhwc(const float* src, int ld_s, int64_t npix, int C, const float* amax, void* dst, int ld_d, int lo_d,
                       float* inv_scale_vec, int n_vec, void* stream);

@@ -62,6 +62,7 @@ SIGNATURES.update({
     "nbp_psi_train": (_i, [_p, _i, _i, _l, _i, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p]),
     "nbp_att_apply": (_i, [_p, _p, _p, _p, _i, _i, _l, _i, _p, _i, _i, _i, _p, _p]),
     "nbp_bn_bwd": (_i, [_p, _i, _p, _i, _i, _l, _i, _p, _p, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p]),
+    "nbp_bn_bwd_split": (_i, [_p, _i, _p, _i, _i, _l, _i, _p, _p, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _i, _p]),
     "nbp_to_split_nhwc": (_i, [_p, _i, _l, _i, _p, _p, _i, _i, _p, _i, _p]),
     "nbp_to_split_cnhw": (_i, [_p, _p, _i, _i, _l, _i, _i, _i, _i, _p, _p, _l, _l, _p, _p]),
     "nbp_conv_wgrad": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p]),

@@ -213,12 +213,18 @@ __global__ void __launch_bounds__(256) att_apply_kernel(const float* __restrict_
     }
 }
 
+__device__ __forceinline__ void atomic_max_abs(float* addr, float v) {       // non-negative floats order like uints
+    atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(fabsf(v)));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // BatchNorm(+ReLU) backward.  y = act(z*scale+shift), xhat = (z-mean)*invstd, dy_m = dy * (y > 0 if relu)
 //   s1 = sum dy_m, s2 = sum dy_m*xhat ;  dz = gamma*invstd*(dy_m - s1/N - xhat*s2/N) ; dgamma = s2 ; dbeta = s1
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dy, int ld_dy, const __half* __restrict__ z, int ld_z, int lo_z,
                                                             size_t npix, int C, const float* __restrict__ scale, const float* __restrict__ shift,
-                                                            const float* __restrict__ mean, const float* __restrict__ invstd, int relu, double* acc) {
+                                                            const float* __restrict__ mean, const float* __restrict__ invstd, int relu, double* acc,
+                                                            float* amax2 /* optional: [0] = max|dy_m|, [1] = max|xhat| */) {
+    float mx_d = 0.0f, mx_x = 0.0f;
     channel_reduce<2>(npix, C, acc, [&](size_t p, int g, float (*a)[8]) {
         float f[8], d[8];
         ld8(z + p * ld_z + 8 * g, lo_z, f);
@@ -228,25 +234,53 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
             const int c = 8 * g + j;
             const float y = fmaf(f[j], scale[c], shift[c]);
             const float dm = (relu && !(y > 0.0f)) ? 0.0f : d[j];
+            const float xh = (f[j] - mean[c]) * invstd[c];
             a[0][j] += dm;
-            a[1][j] = fmaf(dm, (f[j] - mean[c]) * invstd[c], a[1][j]);
+            a[1][j] = fmaf(dm, xh, a[1][j]);
+            mx_d = fmaxf(mx_d, fabsf(dm)); mx_x = fmaxf(mx_x, fabsf(xh));
         }
     });
+    if (amax2) {
+        for (int d = 16; d > 0; d >>= 1) { mx_d = fmaxf(mx_d, __shfl_xor_sync(0xffffffffu, mx_d, d)); mx_x = fmaxf(mx_x, __shfl_xor_sync(0xffffffffu, mx_x, d)); }
+        if (lane_id() == 0) { atomic_max_abs(amax2, mx_d); atomic_max_abs(amax2 + 1, mx_x); }
+    }
 }
 
-__device__ __forceinline__ void atomic_max_abs(float* addr, float v) {       // non-negative floats order like uints
-    atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(fabsf(v)));
+__device__ __forceinline__ float pow2_scale_for(float amax) {
+    if (!(amax > 0.0f) || !isfinite(amax)) return 1.0f;
+    int e; frexpf(amax, &e);                    // amax = m * 2^e, m in [0.5, 1)
+    return ldexpf(1.0f, 8 - e);                 // amax * scale in [128, 256)
 }
 
+// Split mode (dzs != nullptr): dz goes straight out as the fp16x2 GEMM operand of dgrad / wgrad, scaled by a power of two
+// derived from an upper BOUND of max|dz| (from the reduce pass: gamma*invstd*(max|dy_m| + |s1|/N + max|xhat|*|s2|/N)),
+// so no fp32 dz tensor and no separate re-split pass exist.
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ dy, int ld_dy, const __half* __restrict__ z, int ld_z, int lo_z,
                                                            size_t npix, int C, const float* __restrict__ scale, const float* __restrict__ shift,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                            int relu, const double* __restrict__ acc, float* __restrict__ dz, int ld_dz, float* amax,
-                                                           float* dgamma, float* dbeta) {
+                                                           float* dgamma, float* dbeta,
+                                                           __half* __restrict__ dzs, int ld_s, int lo_s, const float* __restrict__ amax2,
+                                                           float* inv_scale_vec, int n_vec) {
     const int G = C >> 3;
     const size_t total = npix * G;
     const float invn = 1.0f / (float)npix;
     float local_max = 0.0f;
+    float sc = 1.0f;
+    if (dzs) {
+        __shared__ float s_b[8];
+        float b = 0.0f;
+        const float md = amax2[0], mxh = amax2[1];
+        for (int c = threadIdx.x; c < C; c += blockDim.x)
+            b = fmaxf(b, fabsf(gamma[c]) * invstd[c] * (md + fabsf((float)acc[c]) * invn + mxh * fabsf((float)acc[C + c]) * invn));
+        for (int d = 16; d > 0; d >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, d));
+        if (lane_id() == 0) s_b[threadIdx.x >> 5] = b;
+        __syncthreads();
+        b = 0.0f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) b = fmaxf(b, s_b[i]);
+        sc = pow2_scale_for(b);
+        if (blockIdx.x == 0 && inv_scale_vec) for (int i = threadIdx.x; i < n_vec; i += blockDim.x) inv_scale_vec[i] = 1.0f / sc;
+    }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t p = i / G; const int g = (int)(i - p * G);
         float f[8], d[8], o[8];
@@ -261,7 +295,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
             o[j] = gamma[c] * invstd[c] * (dm - (float)acc[c] * invn - xh * (float)acc[C + c] * invn);
             local_max = fmaxf(local_max, fabsf(o[j]));
         }
-        st8f(dz + p * ld_dz + 8 * g, o);
+        if (dzs) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] *= sc;
+            st8(dzs + p * ld_s + 8 * g, lo_s, o);
+        } else {
+            st8f(dz + p * ld_dz + 8 * g, o);
+        }
     }
     for (int d = 16; d > 0; d >>= 1) local_max = fmaxf(local_max, __shfl_xor_sync(0xffffffffu, local_max, d));
     if (lane_id() == 0 && amax) atomic_max_abs(amax, local_max);
@@ -273,12 +313,6 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 // GEMM operand preparation: fp32 NHWC gradient -> fp16x2 split, scaled by 2^k so that amax lands near 2^8.
 // *inv_scale_out (device) receives 2^-k for the GEMM epilogue.  Two layouts: NHWC (dgrad A operand) and channel-major
 // CNHW [C][n][h][w] (wgrad operands, K = pixels contiguous).
-__device__ __forceinline__ float pow2_scale_for(float amax) {
-    if (!(amax > 0.0f) || !isfinite(amax)) return 1.0f;
-    int e; frexpf(amax, &e);                    // amax = m * 2^e, m in [0.5, 1)
-    return ldexpf(1.0f, 8 - e);                 // amax * scale in [128, 256)
-}
-
 __global__ void __launch_bounds__(256) to_split_nhwc_kernel(const float* __restrict__ src, int ld_s, size_t npix, int C, const float* __restrict__ amax,
                                                             __half* __restrict__ dst, int ld_d, int lo_d, float* inv_scale_vec, int n_vec) {
     const float sc = amax ? pow2_scale_for(amax[0]) : 1.0f;
@@ -532,15 +566,24 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
         const int img = (int)(p / hw); const int rem = (int)(p - (size_t)img * hw);
         const int y = rem / w, xx = rem - y * w;
         const float2 d = *reinterpret_cast<const float2*>(dz + p * 64 + 2 * lane);
-        if (d.x == 0.0f && d.y == 0.0f) { if (__all_sync(0xffffffffu, d.x == 0.0f && d.y == 0.0f)) continue; }
-        for (int tap = 0; tap < 9; ++tap) {
-            const int yy = y + tap / 3 - 1, xc = xx + tap % 3 - 1;
-            if (yy < 0 || yy >= h || xc < 0 || xc >= w) continue;
-            for (int ci = 0; ci < cin; ++ci) {
-                const float v = __ldg(x + ((size_t)img * cin + ci) * hw + (size_t)yy * w + xc);
-                if (v == 0.0f) continue;
-                atomicAdd(&s_acc[(tap * cin + ci) * 64 + 2 * lane], v * d.x);
-                atomicAdd(&s_acc[(tap * cin + ci) * 64 + 2 * lane + 1], v * d.y);
+        if (__all_sync(0xffffffffu, d.x == 0.0f && d.y == 0.0f)) continue;
+        // the 9*cin input values of this pixel's 3x3 neighbourhood, one per lane; the count images are sparse, so only
+        // the non-zero ones (ballot) are multiplied into the shared accumulator
+        for (int base = 0; base < nk; base += 32) {
+            const int k = base + lane;
+            float v = 0.0f;
+            if (k < nk) {
+                const int tap = k / cin, ci = k - tap * cin;
+                const int yy = y + tap / 3 - 1, xc = xx + tap % 3 - 1;
+                if (yy >= 0 && yy < h && xc >= 0 && xc < w) v = __ldg(x + ((size_t)img * cin + ci) * hw + (size_t)yy * w + xc);
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, v != 0.0f);
+            while (mask) {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float vv = __shfl_sync(0xffffffffu, v, b);
+                atomicAdd(&s_acc[(base + b) * 64 + 2 * lane], vv * d.x);
+                atomicAdd(&s_acc[(base + b) * 64 + 2 * lane + 1], vv * d.y);
             }
         }
     }
@@ -661,18 +704,30 @@ extern "C" int nbp_att_apply(const float* zpsi, const float* psi_scale, const fl
 extern "C" int nbp_bn_bwd(const float* dy, int ld_dy, const void* z, int ld_z, int lo_z, int64_t npix, int C, const float* scale, const float* shift,
                           const float* mean, const float* invstd, const float* gamma, int relu, float* dz, int ld_dz, float* amax /* zeroed here */,
                           float* dgamma, float* dbeta, double* workspace /* [2C] */, void* stream) {
-    if (!dy || !z || !scale || !shift || !mean || !invstd || !gamma || !dz || !workspace) return invalid("nbp_bn_bwd: null pointer argument");
+    return nbp_bn_bwd_split(dy, ld_dy, z, ld_z, lo_z, npix, C, scale, shift, mean, invstd, gamma, relu, dz, ld_dz, amax, dgamma, dbeta, workspace,
+                            nullptr, 0, 0, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int nbp_bn_bwd_split(const float* dy, int ld_dy, const void* z, int ld_z, int lo_z, int64_t npix, int C, const float* scale, const float* shift,
+                                const float* mean, const float* invstd, const float* gamma, int relu, float* dz, int ld_dz, float* amax,
+                                float* dgamma, float* dbeta, double* workspace, void* dz_split, int ld_s, int lo_s, float* amax2 /* [2] scratch */,
+                                float* inv_scale_vec, int n_vec, void* stream) {
+    if (!dy || !z || !scale || !shift || !mean || !invstd || !gamma || (!dz && !dz_split) || !workspace) return invalid("nbp_bn_bwd: null pointer argument");
+    if (dz_split && (!amax2 || lo_s < C || ld_s < lo_s + C || ld_s % 8 || lo_s % 8)) return invalid("nbp_bn_bwd_split: bad split destination (ld=%d lo=%d C=%d)", ld_s, lo_s, C);
     int rc = chk_c("nbp_bn_bwd", C);
     if (rc) return rc;
+    if (dz_split) { rc = check_cuda(cudaMemsetAsync(amax2, 0, 2 * sizeof(float), ST), "memset"); if (rc) return rc; }
     rc = check_cuda(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * C, ST), "memset");
     if (rc) return rc;
     if (amax) { rc = check_cuda(cudaMemsetAsync(amax, 0, sizeof(float), ST), "memset"); if (rc) return rc; }
     const size_t smem = sizeof(float) * (size_t)(256 / (C / 8)) * 2 * C;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); attr = true; }
-    bn_bwd_reduce_kernel<<<red_grid(npix, C), 256, smem, ST>>>(dy, ld_dy, H16(z), ld_z, lo_z, (size_t)npix, C, scale, shift, mean, invstd, relu, workspace);
+    bn_bwd_reduce_kernel<<<red_grid(npix, C), 256, smem, ST>>>(dy, ld_dy, H16(z), ld_z, lo_z, (size_t)npix, C, scale, shift, mean, invstd, relu, workspace,
+                                                               dz_split ? amax2 : nullptr);
     bn_bwd_apply_kernel<<<tk_grid((size_t)npix * (C / 8), 256), 256, 0, ST>>>(dy, ld_dy, H16(z), ld_z, lo_z, (size_t)npix, C, scale, shift, mean, invstd,
-                                                                               gamma, relu, workspace, dz, ld_dz, amax, dgamma, dbeta);
+                                                                               gamma, relu, workspace, dz, ld_dz, amax, dgamma, dbeta,
+                                                                               (__half*)dz_split, ld_s, lo_s, amax2, inv_scale_vec, n_vec);
     count_launch(4);
     return check_cuda(cudaGetLastError(), "nbp_bn_bwd launch");
 }

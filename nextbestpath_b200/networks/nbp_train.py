@@ -34,8 +34,9 @@ def _st():
 class _Tape:
     """Everything one forward pass saves for its backward pass."""
 
-    def __init__(self, dev, B):
+    def __init__(self, dev, B, cache=None):
         self.dev, self.B = dev, B
+        self.cache = cache if cache is not None else {}     # packed GEMM weights, valid until the parameters change
         self.L = _lib.lib()
         self.ws = torch.zeros(2 * 2048 + 16, dtype=torch.float64, device=dev)        # fp64 reduction scratch
         self.ws_big = torch.zeros(9 * 16 * 64 + 8 * 256 + 64, dtype=torch.float64, device=dev)
@@ -71,10 +72,21 @@ def _chk(rc, what):
     _lib.check(rc, what)
 
 
-def _raw_conv(t, w2d, bias, src, taps, dst):
+def _packed(t, key, make):
+    """Packed fp16x2 GEMM weights are a pure function of the parameter: computed once per optimizer step, reused by every
+    micro-batch (the reference accumulates 8 micro-batches per step, nbp_utils.py:387-390)."""
+    w = t.cache.get(key)
+    if w is None:
+        w = make()
+        t.cache[key] = w
+    return w
+
+
+def _raw_conv(t, name, w, bias, src, taps, dst):
     """dst = conv(src) + bias (no normalisation): the raw pre-BatchNorm tensor z."""
     pk = {"precise": True}
-    layer = {"w": M._pack_gemm_weight(w2d, True), "scale": torch.ones_like(bias), "shift": bias.contiguous(), "c_out": w2d.shape[0]}
+    layer = {"w": _packed(t, ("fwd", name), lambda: M._pack_gemm_weight(_w2d(w), True)), "scale": torch.ones_like(bias),
+             "shift": bias.contiguous(), "c_out": w.shape[0]}
     M._conv(pk, layer, t.B, src, taps, dst, relu=False, k_chunk=TRAIN_K_CHUNK)
     return layer
 
@@ -100,20 +112,34 @@ def _dgrad_w2d(w):
     return w.flip(2, 3).permute(1, 2, 3, 0).reshape(w.shape[1], -1)
 
 
-def _conv_backward(t, name, w, src, dz, amax, taps, need_dsrc=True):
-    """Given dz (fp32 [npix, Cout]) of z = conv(src, w): accumulate dW into the parameter gradient, return d(src)."""
+def _new_dz_operand(t, h, wd, cout, cin):
+    """fp16x2 NHWC buffer for dz as a GEMM operand (channels padded to a multiple of 64: Att2_2 has 32) + the inverse-scale vector."""
+    kpad = (cout + 63) // 64 * 64
+    if kpad != cout:
+        dzs = M._Act(torch.zeros((t.B, h, wd, 2 * kpad), dtype=torch.float16, device=t.dev), kpad, 2 * kpad, kpad, h, wd)
+    else:
+        dzs = t.new(h, wd, cout)
+    return dzs, t.f32(max(cin, 1))
+
+
+def _bn_bwd_to_operand(t, dy, z, npix, cout, cin, stats, bnp, bn_name, relu, h, wd):
+    """BatchNorm(+ReLU) backward whose output IS the scaled fp16x2 operand of the following dgrad / wgrad GEMMs."""
+    dzs, inv_vec = _new_dz_operand(t, h, wd, cout, cin)
+    amax2 = t.f32(2)
+    _chk(t.L.nbp_bn_bwd_split(dy.data_ptr(), dy.stride(0), z.ptr, z.ld, z.lo, npix, cout, stats[2].data_ptr(), stats[3].data_ptr(),
+                              stats[0].data_ptr(), stats[1].data_ptr(), bnp["weight"].data_ptr(), 1 if relu else 0, None, 0, None,
+                              t.pgrad(bn_name + ".weight", bnp["weight"]).data_ptr(), t.pgrad(bn_name + ".bias", bnp["bias"]).data_ptr(),
+                              t.ws.data_ptr(), dzs.ptr, dzs.ld, dzs.lo, amax2.data_ptr(), inv_vec.data_ptr(), inv_vec.numel(), _st()), "nbp_bn_bwd_split")
+    return dzs, inv_vec
+
+
+def _conv_backward(t, name, w, src, dzs, inv_vec, taps, need_dsrc=True):
+    """Given dz of z = conv(src, w) as a scaled fp16x2 operand (+ its inverse scale): accumulate dW into the parameter gradient,
+    return d(src) (fp32 NHWC)."""
     B, h, wd = t.B, src.h, src.w
     npix = B * h * wd
     cout, cin = w.shape[0], src.c
-    # ---- dz as a GEMM operand: fp16x2 NHWC, scaled by a power of two; channels padded to a multiple of 64 (Att2_2: 32)
-    kpad = (cout + 63) // 64 * 64
-    if kpad != cout:
-        dzs = M._Act(torch.zeros((B, h, wd, 2 * kpad), dtype=torch.float16, device=t.dev), kpad, 2 * kpad, kpad, h, wd)
-    else:
-        dzs = t.new(h, wd, cout)
-    inv_vec = t.f32(max(cin, 1))
-    _chk(t.L.nbp_to_split_nhwc(dz.data_ptr(), cout, npix, cout, amax.data_ptr(), dzs.ptr, dzs.ld, dzs.lo, inv_vec.data_ptr(), cin, _st()),
-         "nbp_to_split_nhwc")
+    kpad = dzs.c
     # ---- weight gradient: tcgen05 GEMM over the pixel dimension, operands read in place (MN-major)
     dW = t.zeros(kpad, taps, cin)
     _chk(t.L.nbp_conv_wgrad(dzs.ptr, kpad, dzs.ld, dzs.lo, src.ptr, cin, src.ld, src.lo, B, h, wd, taps, inv_vec.data_ptr(),
@@ -124,12 +150,15 @@ def _conv_backward(t, name, w, src, dz, amax, taps, need_dsrc=True):
     if not need_dsrc:
         return None
     # ---- data gradient: the forward conv kernel on flipped / transposed weights, fp32 epilogue
-    wd2 = _dgrad_w2d(w)
-    if kpad != cout:
-        assert taps == 1
-        wd2 = torch.cat((wd2, torch.zeros(cin, kpad - cout, device=t.dev)), dim=1)
+    def make_dgrad():
+        wd2 = _dgrad_w2d(w)
+        if kpad != cout:
+            assert taps == 1
+            wd2 = torch.cat((wd2, torch.zeros(cin, kpad - cout, device=t.dev)), dim=1)
+        return M._pack_gemm_weight(wd2, True)
+
     dsrc = t.f32(npix, cin)
-    layer = {"w": M._pack_gemm_weight(wd2, True), "scale": inv_vec, "shift": t.zeros(cin), "c_out": cin}
+    layer = {"w": _packed(t, ("dgrad", name), make_dgrad), "scale": inv_vec, "shift": t.zeros(cin), "c_out": cin}
     d = _lib.ConvDesc(1, dzs.ptr, kpad, dzs.ld, dzs.lo, None, 0, 0, 0, B, h, wd, taps, 0, layer["w"].data_ptr(), cin,
                       layer["scale"].data_ptr(), layer["shift"].data_ptr(), 0, dsrc.data_ptr(), cin, 0, 0, 1, TRAIN_K_CHUNK)
     _chk(t.L.nbp_conv_fwd(ctypes.byref(d), _st()), "nbp_conv_fwd(dgrad)")
@@ -143,7 +172,7 @@ def _cbr(t, sd, conv, bn, src, taps=9, dst=None, relu=True):
     cout = w.shape[0]
     npix = t.B * src.h * src.w
     z = t.new(src.h, src.w, cout)
-    _raw_conv(t, _w2d(w), b, src, taps, z)
+    _raw_conv(t, conv, w, b, src, taps, z)
     stats = _bn_stats(t, z, npix, bnp)
     y = dst if dst is not None else t.new(src.h, src.w, cout)
     _chk(t.L.nbp_affine_act(z.ptr, z.ld, z.lo, npix, cout, stats[2].data_ptr(), stats[3].data_ptr(), 1 if relu else 0,
@@ -151,22 +180,19 @@ def _cbr(t, sd, conv, bn, src, taps=9, dst=None, relu=True):
 
     def backward(dy, need_dsrc=True):
         """dy: fp32 [npix, ld_dy] view (first `cout` columns used).  Returns d(src) fp32 [npix, cin]."""
-        dz, amax = t.f32(npix, cout), t.f32(1)
-        _chk(t.L.nbp_bn_bwd(dy.data_ptr(), dy.stride(0), z.ptr, z.ld, z.lo, npix, cout, stats[2].data_ptr(), stats[3].data_ptr(),
-                            stats[0].data_ptr(), stats[1].data_ptr(), bnp["weight"].data_ptr(), 1 if relu else 0, dz.data_ptr(), cout,
-                            amax.data_ptr(), t.pgrad(bn + ".weight", bnp["weight"]).data_ptr(), t.pgrad(bn + ".bias", bnp["bias"]).data_ptr(),
-                            t.ws.data_ptr(), _st()), "nbp_bn_bwd")
-        return _conv_backward(t, conv, w, src, dz, amax, taps, need_dsrc)
+        dzs, inv_vec = _bn_bwd_to_operand(t, dy, z, npix, cout, src.c, stats, bnp, bn, relu, src.h, src.w)
+        return _conv_backward(t, conv, w, src, dzs, inv_vec, taps, need_dsrc)
 
     return y, backward
 
 
-def forward_train(sd, x):
+def forward_train(sd, x, cache=None):
     """sd: name -> CUDA fp32 tensor (parameters and BatchNorm buffers; buffers are updated in place).
+    ``cache``: dict that outlives the call and holds the packed GEMM weights (the caller drops it when parameters change).
     Returns (out1, out2, tape)."""
     dev = x.device
     B, cin0, S, S2 = x.shape
-    t = _Tape(dev, B)
+    t = _Tape(dev, B, cache)
     L = t.L
     st = _st()
 
@@ -222,8 +248,8 @@ def forward_train(sd, x):
         wx, bx = sd[f"Att{tg}.W_x.0.weight"], sd[f"Att{tg}.W_x.0.bias"]
         f_int = wg.shape[0]
         zg, zx = t.new(h2, w2, f_int), t.new(h2, w2, f_int)
-        _raw_conv(t, _w2d(wg), bg, g, 1, zg)
-        _raw_conv(t, _w2d(wx), bx, skip, 1, zx)
+        _raw_conv(t, f"Att{tg}.W_g.0", wg, bg, g, 1, zg)
+        _raw_conv(t, f"Att{tg}.W_x.0", wx, bx, skip, 1, zx)
         bng = {k: sd[f"Att{tg}.W_g.1.{k}"] for k in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")}
         bnx = {k: sd[f"Att{tg}.W_x.1.{k}"] for k in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")}
         bn1 = {k: sd[f"Att{tg}.psi.1.{k}"] for k in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")}
@@ -257,14 +283,10 @@ def forward_train(sd, x):
                                t.ws_big.data_ptr(), st), "nbp_att_bwd")
             t.pgrad(f"Att{tg}.psi.0.bias", b_psi)
             # the two branch BatchNorms (no ReLU of their own: the ReLU mask is already in dpre)
-            dzg, amg, dzx, amx = t.f32(npix, f_int), t.f32(1), t.f32(npix, f_int), t.f32(1)
-            for (zz, ss, bnp, name, dzz, am) in ((zg, sg, bng, f"Att{tg}.W_g.1", dzg, amg), (zx, sx, bnx, f"Att{tg}.W_x.1", dzx, amx)):
-                _chk(L.nbp_bn_bwd(dpre.data_ptr(), f_int, zz.ptr, zz.ld, zz.lo, npix, f_int, ss[2].data_ptr(), ss[3].data_ptr(), ss[0].data_ptr(),
-                                  ss[1].data_ptr(), bnp["weight"].data_ptr(), 0, dzz.data_ptr(), f_int, am.data_ptr(),
-                                  t.pgrad(name + ".weight", bnp["weight"]).data_ptr(), t.pgrad(name + ".bias", bnp["bias"]).data_ptr(),
-                                  t.ws.data_ptr(), st), "nbp_bn_bwd(att)")
-            dg = _conv_backward(t, f"Att{tg}.W_g.0", wg, g, dzg, amg, 1)
-            dxs = _conv_backward(t, f"Att{tg}.W_x.0", wx, skip, dzx, amx, 1)
+            dzg, ivg = _bn_bwd_to_operand(t, dpre, zg, npix, f_int, g.c, sg, bng, f"Att{tg}.W_g.1", False, h2, w2)
+            dzx, ivx = _bn_bwd_to_operand(t, dpre, zx, npix, f_int, skip.c, sx, bnx, f"Att{tg}.W_x.1", False, h2, w2)
+            dg = _conv_backward(t, f"Att{tg}.W_g.0", wg, g, dzg, ivg, 1)
+            dxs = _conv_backward(t, f"Att{tg}.W_x.0", wx, skip, dzx, ivx, 1)
             _chk(L.nbp_add_f32(dskip.data_ptr(), dxs.data_ptr(), f_l, npix, f_l, st), "nbp_add_f32")
             # d(up-conv output) = concat half + gate branch
             _chk(L.nbp_add_f32(dg.data_ptr(), dcat[:, f_l:].data_ptr(), 2 * f_l, npix, f_l, st), "nbp_add_f32")
@@ -326,7 +348,11 @@ def forward_train(sd, x):
                  "nbp_maxpool2x2_bwd")
         dy0 = enc_bw[1][0](t.grads.pop(id(x1)))
         stem_backward(dy0)
-        return t.pgrads
+        pg = t.pgrads
+        # the backward closures reference the tape and each other: drop them now so that the activations are returned to the
+        # allocator before the next micro-batch starts (otherwise they wait for Python's cycle collector and the pool grows)
+        t.ops.clear(); t.grads.clear(); enc_bw.clear(); skips.clear(); t.run_backward = None
+        return pg
 
     t.run_backward = run_backward
     return out1, out2, t
@@ -338,7 +364,13 @@ class NBPTrainFunction(torch.autograd.Function):
         sd = dict(zip(names, params))
         for k, v in module.named_buffers():
             sd[k] = v
-        out1, out2, tape = forward_train(sd, x.contiguous().float())
+        # packed weights survive across micro-batches until an in-place update (optimizer.step, load_state_dict) bumps a version
+        key = (str(x.device),) + tuple((p.data_ptr(), p._version) for p in params)
+        cache = getattr(module, "_train_pack", None)
+        if cache is None or cache.get("key") != key:
+            cache = {"key": key}
+            module._train_pack = cache
+        out1, out2, tape = forward_train(sd, x.contiguous().float(), cache)
         ctx.tape, ctx.names, ctx.params = tape, names, params
         return out1, out2
 

@@ -50,7 +50,11 @@ def test_conv_backward_kernels(n, h, w, cin, cout, taps):
     src = _act_split(x)
     dz_nhwc = dz.permute(0, 2, 3, 1).reshape(-1, cout).contiguous().to(DEV)
     amax = dz_nhwc.abs().max().reshape(1).contiguous()
-    dsrc = T._conv_backward(tape, "layer", wt.to(DEV), src, dz_nhwc, amax, taps)
+    # dz as the scaled fp16x2 GEMM operand (in the network nbp_bn_bwd_split writes it directly; here the stand-alone converter)
+    dzs, inv_vec = T._new_dz_operand(tape, h, w, cout, cin)
+    T._chk(tape.L.nbp_to_split_nhwc(dz_nhwc.data_ptr(), cout, n * h * w, cout, amax.data_ptr(), dzs.ptr, dzs.ld, dzs.lo, inv_vec.data_ptr(), inv_vec.numel(),
+                                    torch.cuda.current_stream().cuda_stream), "nbp_to_split_nhwc")
+    dsrc = T._conv_backward(tape, "layer", wt.to(DEV), src, dzs, inv_vec, taps)
     torch.cuda.synchronize()
     dW = tape.pgrads["layer.weight"].cpu()
     rel = lambda a, b: float((a.double() - b).norm() / b.norm())
