@@ -225,16 +225,25 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
                                                             const float* __restrict__ mean, const float* __restrict__ invstd, int relu, double* acc,
                                                             float* amax2 /* optional: [0] = max|dy_m|, [1] = max|xhat| */) {
     float mx_d = 0.0f, mx_x = 0.0f;
+    // per-channel (scale, shift, mean, invstd) staged in shared memory behind channel_reduce's scratch ([lanes][2][C])
+    extern __shared__ float s_red[];
+    float* s_co = s_red + (size_t)(blockDim.x / (C >> 3)) * 2 * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { s_co[c] = scale[c]; s_co[C + c] = shift[c]; s_co[2 * C + c] = mean[c]; s_co[3 * C + c] = invstd[c]; }
+    __syncthreads();
     channel_reduce<2>(npix, C, acc, [&](size_t p, int g, float (*a)[8]) {
-        float f[8], d[8];
+        float f[8], d[8], co[4][8];
         ld8(z + p * ld_z + 8 * g, lo_z, f);
         ld8f(dy + p * ld_dy + 8 * g, d);
 #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 u = *reinterpret_cast<const float4*>(s_co + q * C + 8 * g), v = *reinterpret_cast<const float4*>(s_co + q * C + 8 * g + 4);
+            co[q][0] = u.x; co[q][1] = u.y; co[q][2] = u.z; co[q][3] = u.w; co[q][4] = v.x; co[q][5] = v.y; co[q][6] = v.z; co[q][7] = v.w;
+        }
+#pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = 8 * g + j;
-            const float y = fmaf(f[j], scale[c], shift[c]);
+            const float y = fmaf(f[j], co[0][j], co[1][j]);
             const float dm = (relu && !(y > 0.0f)) ? 0.0f : d[j];
-            const float xh = (f[j] - mean[c]) * invstd[c];
+            const float xh = (f[j] - co[2][j]) * co[3][j];
             a[0][j] += dm;
             a[1][j] = fmaf(dm, xh, a[1][j]);
             mx_d = fmaxf(mx_d, fabsf(dm)); mx_x = fmaxf(mx_x, fabsf(xh));
@@ -281,18 +290,30 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
         sc = pow2_scale_for(b);
         if (blockIdx.x == 0 && inv_scale_vec) for (int i = threadIdx.x; i < n_vec; i += blockDim.x) inv_scale_vec[i] = 1.0f / sc;
     }
+    // per-channel coefficients staged once per block in shared memory ([7][C]: scale, shift, mean, invstd, k = gamma*invstd,
+    // a1 = s1/N, a2 = s2/N): the element loop then issues 16-byte LDS instead of 7 scalar global loads per channel
+    extern __shared__ float s_co[];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        s_co[c] = scale[c]; s_co[C + c] = shift[c]; s_co[2 * C + c] = mean[c]; s_co[3 * C + c] = invstd[c];
+        s_co[4 * C + c] = gamma[c] * invstd[c]; s_co[5 * C + c] = (float)acc[c] * invn; s_co[6 * C + c] = (float)acc[C + c] * invn;
+    }
+    __syncthreads();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t p = i / G; const int g = (int)(i - p * G);
-        float f[8], d[8], o[8];
+        float f[8], d[8], o[8], co[7][8];
         ld8(z + p * ld_z + 8 * g, lo_z, f);
         ld8f(dy + p * ld_dy + 8 * g, d);
 #pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            const float4 u = *reinterpret_cast<const float4*>(s_co + q * C + 8 * g), v = *reinterpret_cast<const float4*>(s_co + q * C + 8 * g + 4);
+            co[q][0] = u.x; co[q][1] = u.y; co[q][2] = u.z; co[q][3] = u.w; co[q][4] = v.x; co[q][5] = v.y; co[q][6] = v.z; co[q][7] = v.w;
+        }
+#pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = 8 * g + j;
-            const float y = fmaf(f[j], scale[c], shift[c]);
+            const float y = fmaf(f[j], co[0][j], co[1][j]);
             const float dm = (relu && !(y > 0.0f)) ? 0.0f : d[j];
-            const float xh = (f[j] - mean[c]) * invstd[c];
-            o[j] = gamma[c] * invstd[c] * (dm - (float)acc[c] * invn - xh * (float)acc[C + c] * invn);
+            const float xh = (f[j] - co[2][j]) * co[3][j];
+            o[j] = co[4][j] * (dm - co[5][j] - xh * co[6][j]);
             local_max = fmaxf(local_max, fabsf(o[j]));
         }
         if (dzs) {
@@ -720,12 +741,16 @@ extern "C" int nbp_bn_bwd_split(const float* dy, int ld_dy, const void* z, int l
     rc = check_cuda(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * C, ST), "memset");
     if (rc) return rc;
     if (amax) { rc = check_cuda(cudaMemsetAsync(amax, 0, sizeof(float), ST), "memset"); if (rc) return rc; }
-    const size_t smem = sizeof(float) * (size_t)(256 / (C / 8)) * 2 * C;
+    const size_t smem = sizeof(float) * ((size_t)(256 / (C / 8)) * 2 * C + 4 * (size_t)C);
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); attr = true; }
+    if (!attr) {
+        cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(bn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 2048 * 4);
+        attr = true;
+    }
     bn_bwd_reduce_kernel<<<red_grid(npix, C), 256, smem, ST>>>(dy, ld_dy, H16(z), ld_z, lo_z, (size_t)npix, C, scale, shift, mean, invstd, relu, workspace,
                                                                dz_split ? amax2 : nullptr);
-    bn_bwd_apply_kernel<<<tk_grid((size_t)npix * (C / 8), 256), 256, 0, ST>>>(dy, ld_dy, H16(z), ld_z, lo_z, (size_t)npix, C, scale, shift, mean, invstd,
+    bn_bwd_apply_kernel<<<tk_grid((size_t)npix * (C / 8), 256), 256, sizeof(float) * 7 * (size_t)C, ST>>>(dy, ld_dy, H16(z), ld_z, lo_z, (size_t)npix, C, scale, shift, mean, invstd,
                                                                                gamma, relu, workspace, dz, ld_dz, amax, dgamma, dbeta,
                                                                                (__half*)dz_split, ld_s, lo_s, amax2, inv_scale_vec, n_vec);
     count_launch(4);
