@@ -264,6 +264,23 @@ int nbp_candidate_scores(const float* cand, const int32_t* n_cand, int max_cand,
                          const float* value_map, int n_ch, int Sv, const float* full_proj, int S, int n,
                          float range_lo, float range_hi, int window, float* value, float* density, int32_t* cell, uint8_t* valid, void* stream);
 
+/* ------------------------------------------------------------------------------------------ SURVEY section 8(f) row 2
+ * calculate_coverage_percentage (next_best_path/utility/long_term_utils.py:437-468; called every pose at
+ * next_best_path/testers/nbp_planning.py:71 and next_best_path/utility/nbp_utils.py:572), for n_scenes scenes in one call:
+ *   coverage[b] = mean_i [ min_j || gt_b[i] - sampled_b[j] || < threshold ],
+ *   sampled_b = cloud_b if len <= weight*G_b, else a uniform random subset of weight*G_b points (sample_idx [n, sample_stride]
+ *   int64 gives the subset explicitly -- e.g. torch.randperm(len)[:k] for the reference's own stream; NULL = keyed permutation).
+ * The ground truth comes bucketed into a uniform grid of edge `cell` >= threshold (built once per scene by the caller):
+ * gt_sorted [sum G][3] points ordered by cell index (z*ny + y)*nx + x, gt_off [n+1]; cell_start = per scene ncells+1 scene-local
+ * starts, cell_off [n+1]; origin [n][3], dims [n][3] = (nx, ny, nz); cell of a point = floor((p - origin) * (1/cell)) in fp32.
+ * covered [sum G] bytes = scratch (zeroed here, 1 where the ground-truth point is covered); counts (may be NULL) = covered
+ * points per scene.  A scene with an empty cloud reports 0 (long_term_utils.py:461-462). */
+int nbp_coverage_percentage(const float* cloud, int64_t cloud_stride, const int32_t* cloud_len, const int64_t* sample_idx,
+                            int64_t sample_stride, const float* gt_sorted, const int64_t* gt_off, const int32_t* cell_start,
+                            const int64_t* cell_off, const float* origin, const int32_t* dims, int n_scenes, int64_t max_samples,
+                            int64_t total_gt, float cell, float threshold, int weight, uint64_t seed, uint8_t* covered,
+                            float* coverage, int32_t* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

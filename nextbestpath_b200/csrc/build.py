@@ -17,6 +17,7 @@ SOURCES = {
     "backproject.cu": ["-fmad=false"],
     "scatter.cu": ["-fmad=false"],
     "planner.cu": ["-fmad=false"],
+    "coverage.cu": ["-fmad=false"],
     "conv_tc.cu": [],
     "nn_kernels.cu": [],
     "train_kernels.cu": [],

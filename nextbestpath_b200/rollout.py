@@ -155,8 +155,12 @@ class RolloutEngine:
         self.traj_len.fill_(self.traj_len_host)
 
     # ------------------------------------------------------------------ API
-    def reset(self, start_pose):
-        """start_pose (B,5) host tensor (x,y,z,elev,azim): renders the first key frame of every scene."""
+    def reset(self, start_pose, approach_pose=None, approach_az=None, start_az=None):
+        """start_pose (B,5) host tensor (x,y,z,elev,azim): renders the first key frame of every scene.
+        ``approach_pose`` (B,5) + azimuth indices: the reference's set-up code places the camera on a neighbouring lattice pose
+        and walks to the start pose in 4 interpolation steps (macarons/testers/scene.py:466-486), so ``X_cam_history`` -- the
+        trajectory image, channel 4 of the model input -- starts with those 1+4 positions; the 4 set-up frames themselves are
+        never back-projected by the NBP loop.  Without it the trajectory starts at the start pose."""
         start = torch.as_tensor(start_pose, dtype=torch.float32)
         self.cloud_len.zero_(); self.traj_len_host = 0; self.traj_len.zero_(); self.overflow.zero_()
         self.step_idx = 0; self.max_points_bound = 0
@@ -164,7 +168,13 @@ class RolloutEngine:
         self.pose.copy_(start.to(self.dev))
         self.frame_R[0].copy_(R.reshape(-1, 9).to(self.dev)); self.frame_T[0].copy_(T.to(self.dev))
         self._render(self.frame_R[0], self.frame_T[0], self.scene_ids, list(range(self.B)), self.frames[0])
-        self._append_traj(self.pose[:, None, :3])
+        if approach_pose is not None:
+            appr = torch.as_tensor(approach_pose, dtype=torch.float32)
+            steps = interpolated_poses(appr, start, approach_az, start_az)               # (4, B, 5); step 4 == start pose
+            hist = torch.cat((appr[None, :, :3], steps[:, :, :3]), dim=0).permute(1, 0, 2).contiguous()
+            self._append_traj(hist.to(self.dev))
+        else:
+            self._append_traj(self.pose[:, None, :3])
 
     def upload_move(self, cur_pose, next_pose, cur_az, next_az):
         """Host side of stage D: interpolated poses -> (R, T) for the 4 views of every scene, copied to the device

@@ -139,3 +139,24 @@ def test_rollout_host_outputs_overlap_copy():
         torch.cuda.synchronize()
         runs.append((eng.cloud_len.cpu().clone(), out.value_map.cpu().clone()))
     assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+
+
+def test_reset_with_setup_approach_matches_reference_history():
+    """reset(..., approach_pose=...) reproduces the 1+4 set-up positions of the reference's X_cam_history (scene.py:479-486):
+    the trajectory channel of the first model input equals the oracle histogram of [neighbour, 3 interpolated, start]."""
+    scene = syn.make_scene(77, tri_budget=700)
+    poses, az = syn.random_walk(scene, 3, seed=77)
+    net = NBP(); net.load_state_dict(NT.golden_state_dict(seed=9)); net.to(DEV).eval()
+    eng = RolloutEngine([scene], net, DEV, S=S, H=H, W=W, max_steps=3, gathering_factor=1.0, sensor_range=30.0)
+    # walk pose 0 -> pose 1 is the set-up approach; the rollout proper starts at pose 1
+    eng.reset(poses[None, 1], approach_pose=poses[None, 0], approach_az=az[None, 0], start_az=az[None, 1])
+    out = eng.step(eng.upload_move(poses[None, 1], poses[None, 2], az[None, 1], az[None, 2]))
+    hist = [poses[0, :3]] + [O.interpolate_pose(poses[0], poses[1], k, 4, 8, int(az[0]), int(az[1]))[0].numpy() for k in range(1, 5)]
+    assert np.array_equal(hist[-1], poses[1, :3])
+    bounds = O.y_bins_from_verts(torch.from_numpy(scene.verts)).numpy()[:-1]
+    R, T = O.camera_rt(torch.tensor(poses[1:2, :3]), torch.tensor(poses[1:2, 3:]))
+    z = O.render_depth(scene.verts, scene.faces, R[0].numpy(), T[0].numpy(), H, W)[0]
+    cloud = O.partial_point_cloud(z, R[0].numpy(), T[0].numpy(), 30.0, 1.0)
+    grid = O.build_model_input(cloud, poses[1], bounds, np.stack(hist), S)
+    assert np.array_equal(out.model_input[0].cpu().numpy(), grid)
+    assert grid[4].sum() >= 2
