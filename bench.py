@@ -36,6 +36,16 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE line (the JSON): the real stdout is kept aside and fd 1 is pointed at stderr, so that library
+# banners (e.g. "NCCL version ..." printed on communicator creation) cannot end up in front of the result line
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 METRIC = "rollout_scene_steps_per_sec"
 UNIT = "scene-steps/s"
 FLOP_PER_SCENE_STEP = {128: 45.603e9, 256: 182.411e9, 512: 729.645e9}     # conv 2*MAC, SURVEY.md section 6
@@ -177,7 +187,7 @@ def run_reference(args):
             "gpu_launches": 0,
             "note": "oracle port of the reference CPU path: PyTorch3D 0.7.4 naive rasteriser restated in C, numpy un-projection "
                     "and histogram, torch fp32 NBP; pytorch3d/trimesh are not installable here (DESIGN.md)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU leg
@@ -345,7 +355,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "stage_ms": stage_ms,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -184,6 +184,13 @@ class RolloutEngine:
         pin = lambda t: t.contiguous().pin_memory().to(self.dev, non_blocking=True)
         return pin(poses), pin(R.reshape(-1, 9)), pin(T)
 
+    def coverage(self, index, weight: int = 2, seed=None):
+        """calculate_coverage_percentage(gt_scene_pc, full_pc) for every scene (nbp_planning.py:71):
+        ``index`` = nextbestpath_b200.coverage.CoverageIndex over the scenes' ground-truth clouds.  Returns (B,) fp32 on the
+        device; no host synchronisation."""
+        return index.coverage(self.cloud, self.cloud_len, weight=weight, seed=self.seed + self.step_idx if seed is None else seed,
+                              max_points=self.max_points_bound)
+
     def wait_host_outputs(self):
         """Block the host until the read-back started by the last ``step(..., host_out=...)`` has landed.  The device
         keeps running stages D and E of that step meanwhile."""

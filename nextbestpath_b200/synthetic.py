@@ -145,3 +145,17 @@ def random_walk(scene: Scene, n_poses: int, seed: int) -> tuple[np.ndarray, np.n
                 p = q
                 break
     return poses, az_idx
+
+
+def sample_surface(scene: Scene, n_points: int, seed: int) -> np.ndarray:
+    """Area-weighted random points on the mesh surface: the ground-truth cloud the coverage metric compares against
+    (the reference samples `n_gt_surface_points` = 20000 / 50000 of them per scene, macarons_utils.py:612-637)."""
+    rng = np.random.default_rng(seed)
+    tri = scene.verts[scene.faces]                                   # (F, 3, 3)
+    area = 0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1)
+    f = rng.choice(len(tri), size=n_points, p=area / area.sum())
+    u, v = rng.random(n_points), rng.random(n_points)
+    flip = u + v > 1.0
+    u[flip], v[flip] = 1.0 - u[flip], 1.0 - v[flip]
+    p = tri[f, 0] + u[:, None] * (tri[f, 1] - tri[f, 0]) + v[:, None] * (tri[f, 2] - tri[f, 0])
+    return p.astype(np.float32)

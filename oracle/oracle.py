@@ -330,3 +330,33 @@ def score_candidates(value_map, full_proj, candidates, pose, skip=None, S: int =
         valid[j] = True
         score[j] = float(max_gain[r, c]) - 10 * float(dens)
     return valid, cell, score
+
+
+# --------------------------------------------------------------------------- section 8f row 2: coverage metric
+def coverage_percentage(gt, pc, threshold: float = 1.0, weight: int = 2, indices=None, return_flags: bool = False):
+    """calculate_coverage_percentage next_best_path/utility/long_term_utils.py:457-468 (random_sample_pc :436-446,
+    find_nearest_points_distances :448-455): fraction of ground-truth points ``gt`` (G,3) whose nearest point of the
+    (sub-sampled) reconstruction ``pc`` (N,3) is closer than ``threshold``.  If N > weight*G the reference keeps
+    ``pc[torch.randperm(N)[:weight*G]]``: pass that index prefix as ``indices``.  Distances are evaluated in strict fp32 as
+    d2 = (dx*dx + dy*dy) + dz*dz < threshold*threshold (the arithmetic csrc/coverage.cu is pinned to); torch.cdist itself switches
+    to a matmul expansion for large inputs, so the reference is reproducible only to ~1e-3 in distance (tests count the
+    ground-truth points that close to the threshold)."""
+    g = np.ascontiguousarray(np.asarray(gt, dtype=np.float32).reshape(-1, 3))
+    q = np.ascontiguousarray(np.asarray(pc, dtype=np.float32).reshape(-1, 3))
+    if len(q) == 0:
+        return (0.0, np.zeros(len(g), dtype=bool)) if return_flags else 0.0
+    want = int(len(g) * weight)
+    if len(q) > want:
+        if indices is None:
+            raise ValueError("reconstruction longer than weight*G: pass the randperm prefix as `indices`")
+        q = q[np.asarray(indices, dtype=np.int64)[:want]]
+    thr2 = np.float32(threshold) * np.float32(threshold)
+    flags = np.zeros(len(g), dtype=bool)
+    step = max(1, (1 << 24) // max(len(q), 1))
+    for a in range(0, len(g), step):
+        blk = g[a:a + step]
+        dx = blk[:, None, 0] - q[None, :, 0]; dy = blk[:, None, 1] - q[None, :, 1]; dz = blk[:, None, 2] - q[None, :, 2]
+        d2 = (dx * dx + dy * dy) + dz * dz                                       # float32 throughout, this association
+        flags[a:a + step] = (d2 < thr2).any(axis=1)
+    cov = float(np.float32(flags.sum()) / np.float32(len(g))) if len(g) else 0.0
+    return (cov, flags) if return_flags else cov

@@ -26,13 +26,13 @@ def timed(fn, warm=3, it=5):
 
 
 def main():
-    ap = argparse.ArgumentParser(); ap.add_argument("--quick", action="store_true"); a = ap.parse_args()
+    ap = argparse.ArgumentParser(); ap.add_argument("--quick", action="store_true"); ap.add_argument("--only", default=""); a = ap.parse_args()
     H, W, S = 256, 456, 256
     rows = []
     tris_list = [1000, 3000, 10000, 30000, 100000] if not a.quick else [3000, 30000]
     env_list = [128, 256, 512, 1024] if not a.quick else [128, 512]
     # ---- raster + back-projection
-    for F in tris_list:
+    for F in (tris_list if a.only in ("", "raster") else []):
         base = [syn.make_scene(500 + i, tri_budget=F) for i in range(8)]          # 8 distinct meshes, reused round-robin
         for E in env_list:
             if F * E > 30_000_000:                                               # bound the workspace (2*F*E records of 96 B)
@@ -64,7 +64,7 @@ def main():
             del verts, faces, z, cloud
             torch.cuda.empty_cache()
     # ---- grid scatter
-    for N in ([30_000, 300_000, 1_500_000, 3_000_000] if not a.quick else [300_000]):
+    for N in (([30_000, 300_000, 1_500_000, 3_000_000] if not a.quick else [300_000]) if a.only in ("", "scatter") else []):
         for E in env_list:
             if N * E * 12 > 40e9:
                 continue
@@ -82,6 +82,33 @@ def main():
             rows.append({"kernel": "grid_scatter", "points": N, "envs": E, "ms": ms, "GBps": nbytes / ms / 1e6, "frac_of_peak": nbytes / ms / 1e6 / PEAK,
                          "binned_fraction": float(out[:, :4].sum() / (E * N))})
             del cloud, out
+            torch.cuda.empty_cache()
+    # ---- coverage metric: G ground-truth points per scene, clouds of N points (sample = 2*G)
+    from nextbestpath_b200.coverage import CoverageIndex
+    for (G, N) in (([(20000, 300_000), (20000, 1_500_000), (50000, 1_500_000)] if not a.quick else [(20000, 300_000)]) if a.only in ("", "coverage") else []):
+        for E in ([64, 256] if not a.quick else [64]):
+            base = [syn.make_scene(700 + i, "simple") for i in range(8)]
+            gts = [syn.sample_surface(base[i % 8], G, seed=i) for i in range(E)]
+            index = CoverageIndex(gts, DEV, threshold=1.0)
+            cloud = torch.empty((E, N, 3), device=DEV)
+            for i in range(E):                                   # reconstruction = noisy surface samples of a part of the scene
+                sp = torch.from_numpy(syn.sample_surface(base[i % 8], 20000, seed=1000 + i)).to(DEV)
+                sp = sp[sp[:, 0] < sp[:, 0].median()]
+                rep = sp[torch.randint(0, len(sp), (N,), device=DEV)]
+                cloud[i] = rep + torch.randn((N, 3), device=DEV) * 0.05
+            lens = torch.full((E,), N, dtype=torch.int32, device=DEV)
+            out = [None]
+            ms = timed(lambda: out.__setitem__(0, index.coverage(cloud, lens, seed=3)))
+            nbytes = E * (2 * G * 12 + G * 12 + G)                # sampled points + ground truth + flags
+            tic = __import__("time").perf_counter()
+            gt0, pc0 = torch.from_numpy(gts[0]), cloud[0].cpu()
+            smp = pc0[torch.randperm(N)[: 2 * G]]
+            cpu_cov = float((torch.cdist(gt0, smp).min(dim=1).values < 1.0).float().mean())      # the reference's expression, one scene, host cores
+            cpu_ms = (__import__("time").perf_counter() - tic) * 1e3
+            rows.append({"kernel": "coverage", "gt_points": G, "cloud_points": N, "envs": E, "ms": ms, "GBps": nbytes / ms / 1e6,
+                         "frac_of_peak": nbytes / ms / 1e6 / PEAK, "coverage_scene0": float(out[0][0]), "cpu_cdist_scene0": cpu_cov,
+                         "cpu_cdist_ms_per_scene": cpu_ms})
+            del cloud
             torch.cuda.empty_cache()
     print(json.dumps({"hbm_peak_GBps": PEAK, "rows": rows}))
     for r in rows:

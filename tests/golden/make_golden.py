@@ -9,6 +9,8 @@ What is pinned:
                    map_points_to_n_imgs (:198-223), get_point_position_in_the_img (:160-164) and the
                    slab split expressions of next_best_path/testers/nbp_planning.py:114-115,446-451
   nbp_eval.npz   : next_best_path/networks/nbp_model.py NBP.forward in eval mode (S=128, B=1)
+  coverage.npz   : next_best_path/utility/long_term_utils.py calculate_coverage_percentage (:436-468), executed from the reference tree
+                   (``--coverage-only`` regenerates just this file)
   nbp_train.npz  : NBP.forward (train mode) + NBP.loss + backward: loss, per-parameter gradient norms,
                    BN running statistics after the step (S=64, B=2)
 """
@@ -94,6 +96,38 @@ def planner_golden(ru):
     print("planner golden:", len(lst), "valid candidates of", len(keys), "; fused ones", int(ns["predicted_obstacle_map"].sum()))
 
 
+def coverage_golden():
+    """coverage.npz: random_sample_pc / find_nearest_points_distances / calculate_coverage_percentage are
+    EXECUTED from next_best_path/utility/long_term_utils.py:436-468 (the module itself cannot be imported: trimesh, pytorch3d)."""
+    ns = {"torch": torch}
+    exec(_ref_lines("/root/reference/next_best_path/utility/long_term_utils.py", "def random_sample_pc", "return similar_points.item()"), ns)
+    ref = ns["calculate_coverage_percentage"]
+    g = torch.Generator().manual_seed(33)
+    # ground truth: points on the walls / floor of a 60 x 8 x 40 room; reconstruction: noisy samples of part of it
+    def surface(n):
+        u = torch.rand(n, 3, generator=g) * torch.tensor([60.0, 8.0, 40.0])
+        face = torch.randint(0, 5, (n,), generator=g)
+        u[face == 0, 0] = 0.0; u[face == 1, 0] = 60.0; u[face == 2, 2] = 0.0; u[face == 3, 2] = 40.0; u[face == 4, 1] = 0.0
+        return u
+    out = {}
+    gt = surface(3000)
+    for name, n_pc, part in (("sub", 9000, 0.6), ("all", 2500, 0.35)):
+        pc = surface(n_pc)
+        pc = pc[pc[:, 0] < 60.0 * part + 1e-3] if name == "all" else pc
+        pc = pc[: (n_pc if name == "sub" else len(pc))]
+        pc[:, 0] = pc[:, 0] * (part if name == "sub" else 1.0)
+        pc = pc + torch.randn(pc.shape, generator=g) * 0.05
+        torch.manual_seed(1234)
+        val = ref(gt, pc)
+        torch.manual_seed(1234)
+        idx = torch.randperm(len(pc))[: 2 * len(gt)] if len(pc) > 2 * len(gt) else torch.zeros(0, dtype=torch.long)
+        out[f"{name}_pc"] = pc.numpy(); out[f"{name}_idx"] = idx.numpy(); out[f"{name}_cov"] = np.float64(val)
+    out["gt"] = gt.numpy()
+    out["empty_cov"] = np.float64(ref(gt, torch.zeros(0, 3)))
+    np.savez_compressed(os.path.join(HERE, "coverage.npz"), **out)
+    print("coverage.npz:", {k: float(v) for k, v in out.items() if k.endswith("_cov")})
+
+
 def main():
     NBP, ru = import_reference()
     from oracle import nbp_torch as O
@@ -170,10 +204,15 @@ def main():
                         rm_up22=st["Up_conv2_2.conv.4.running_mean"].numpy(),
                         **{"probe_" + k.replace(".", "_"): v for k, v in probe.items()})
     planner_golden(ru)
+    coverage_golden()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
 
+
+if __name__ == "__main__" and "--coverage-only" in sys.argv:
+    coverage_golden()
+    sys.exit(0)
 
 if __name__ == "__main__":
     main()
