@@ -42,7 +42,9 @@ using namespace tc;
 
 static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_K = 64;                         // fp16 elements = one 128-byte swizzle row
-static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;     // one plane of a plain 128-pixel A block
+static constexpr int HALO_ROWS = 160;                          // (th + 2) * tw pixels of a halo block (tw = 16, th = 8)
+static constexpr int A_HALO_BYTES = HALO_ROWS * BLOCK_K * 2;   // one plane of a halo A block
 static constexpr int CONV_THREADS = 256;
 static constexpr int SMEM_LIMIT = 232448;                  // 227 KB opt-in maximum per CTA
 static constexpr int SMEM_AUX = 4096;                      // barriers + tmem ptr + scale/shift staging
@@ -58,17 +60,24 @@ struct ConvKParams {
                                         // registers (round-to-nearest); the tensor core's own accumulator truncates
     int up2x;                           // 1: fused nearest-2x upsample + 3x3 conv as 4 parity-specific 2x2 convs (taps == 4)
     int b_rows_per_parity;              // rows of the weight matrix per parity block (up2x)
+    // K loop geometry.  plain: one stage = one tap x one 64-channel slice (ngroups = taps, gtaps = 1).  halo (HALO kernels): one
+    // stage = the (th+2)-row A block of one column offset dx + the B tiles of its gtaps taps (3x3: 3 groups x 3 taps, up2x: 2 x 2)
+    int ngroups, gtaps;
+    int a_tx;                           // bytes the A loads of one stage deliver
+    int aoff_step;                      // halo: byte offset of one tile row inside the A block (tw * 128)
     const float* scale; const float* shift;
     int relu;
     __half* dst; int dst_ld, dst_c_off, dst_lo_off;
 };
 
-template <int BLOCK_N, bool PRECISE>
+template <int BLOCK_N, bool PRECISE, int HALO>     // HALO = 0: plain stages; 2 | 3: halo stages carrying that many taps
 struct ConvCfg {
     static constexpr int PLANES = PRECISE ? 2 : 1;
-    static constexpr int A_BYTES = PLANES * A_STAGE_BYTES;                 // A_hi [, A_lo]
+    static constexpr int A_PLANE = HALO ? A_HALO_BYTES : A_STAGE_BYTES;
+    static constexpr int A_BYTES = PLANES * A_PLANE;                      // A_hi [, A_lo]
     static constexpr int B_ROWS = PLANES * BLOCK_N;                       // W_hi rows [, W_lo rows]
-    static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
+    static constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 2;             // one tap x one 64-channel slice of the weights
+    static constexpr int B_STAGE_BYTES = (HALO ? HALO : 1) * B_TILE_BYTES;
     static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES_RAW = (SMEM_LIMIT - SMEM_AUX - 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -79,11 +88,11 @@ struct ConvCfg {
     static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
 };
 
-template <int BLOCK_N, bool PRECISE>
+template <int BLOCK_N, bool PRECISE, int HALO>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
               const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
-    using Cfg = ConvCfg<BLOCK_N, PRECISE>;
+    using Cfg = ConvCfg<BLOCK_N, PRECISE, HALO>;
     constexpr int STAGES = Cfg::STAGES;
 
     extern __shared__ uint8_t smem_raw[];
@@ -118,7 +127,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     const int tiles_per_parity = p.m_tiles * p.n_tiles;
     const int num_tiles = (p.up2x ? 4 : 1) * tiles_per_parity;
     const int kc_total = p.kc0 + p.kc1;
-    const int num_k = p.taps * kc_total;
+    const int num_k = p.ngroups * kc_total;                              // stages per output tile (p.kchunk counts stages too)
 
     if (warp == 0) {
         // ================================================================= TMA producer
@@ -134,20 +143,30 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                 const int tb = mt / p.tiles_y;
                 const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tb * p.tn;
                 const int b_row0 = parity * p.b_rows_per_parity + n_tile * Cfg::B_ROWS;
-                for (int tap = 0; tap < p.taps; ++tap) {
+                for (int g = 0; g < p.ngroups; ++g) {
                     int dy = 0, dx = 0;
-                    if (p.up2x) { dy = (tap >> 1) - 1 + (parity >> 1); dx = (tap & 1) - 1 + (parity & 1); }
-                    else if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+                    if (HALO) { dy = -1; dx = g - 1 + (p.up2x ? (parity & 1) : 0); }          // rows y0-1 .. y0+th of column offset dx
+                    else if (p.up2x) { dy = (g >> 1) - 1 + (parity >> 1); dx = (g & 1) - 1 + (parity & 1); }
+                    else if (p.taps == 9) { dy = g / 3 - 1; dx = g % 3 - 1; }
                     for (int kc = 0; kc < kc_total; ++kc) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                         const bool first = kc < p.kc0;
                         const CUtensorMap* tm = first ? &tmA0 : &tmA1;
                         const int c = (first ? kc : kc - p.kc0) * BLOCK_K;
                         uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
+                        uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.a_tx + (uint32_t)Cfg::B_STAGE_BYTES);
                         tma_load_4d(sa, tm, &full_bar[stage], c, x0 + dx, y0 + dy, n0);
-                        if (PRECISE) tma_load_4d(sa + A_STAGE_BYTES, tm, &full_bar[stage], c + (first ? p.lo0 : p.lo1), x0 + dx, y0 + dy, n0);
-                        tma_load_2d(smem_b + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], (tap * kc_total + kc) * BLOCK_K, b_row0);
+                        if (PRECISE) tma_load_4d(sa + Cfg::A_PLANE, tm, &full_bar[stage], c + (first ? p.lo0 : p.lo1), x0 + dx, y0 + dy, n0);
+                        if (HALO) {
+#pragma unroll
+                            for (int j = 0; j < HALO; ++j) {                                   // taps (dy = j-1 | j-1+py) of this column
+                                const int tap = p.up2x ? j * 2 + g : j * 3 + g;
+                                tma_load_2d(sb + j * Cfg::B_TILE_BYTES, &tmB, &full_bar[stage], (tap * kc_total + kc) * BLOCK_K, b_row0);
+                            }
+                        } else {
+                            tma_load_2d(sb, &tmB, &full_bar[stage], (g * kc_total + kc) * BLOCK_K, b_row0);
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -169,17 +188,36 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                 for (int ks = ks0; ks < ks1; ++ks) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES));
-                    const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
+                    const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::A_BYTES);
+                    const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES);
+                    if (HALO) {
+                        // tap j of the column reads the SAME A block from tile row (row0 + j): a multiple of 8 pixel rows = 1024 B,
+                        // so the swizzle phase is unchanged and only the descriptor address moves
+                        const int row0 = p.up2x ? ((tile / tiles_per_parity) >> 1) : 0;
+#pragma unroll
+                        for (int j = 0; j < HALO; ++j) {
+                            const uint64_t adesc = umma_desc_kmajor_sw128(a_addr + (uint32_t)((row0 + j) * p.aoff_step));
+                            const uint64_t alo = umma_desc_kmajor_sw128(a_addr + (uint32_t)((row0 + j) * p.aoff_step) + Cfg::A_PLANE);
+                            const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr + (uint32_t)(j * Cfg::B_TILE_BYTES));
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k) {
+                                umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_main, (ks > ks0 || j > 0 || k > 0) ? 1u : 0u);
+                                if (PRECISE) umma_f16(d_tmem + (uint32_t)BLOCK_N, alo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, 1u);
+                            }
+                        }
+                    } else {
+                    const uint64_t adesc = umma_desc_kmajor_sw128(a_addr);
+                    const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; ++k) {
                         // +32 bytes (16 fp16) along K inside the 128-byte swizzle row: +2 in the encoded address
                         umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_main, (ks > ks0 || k > 0) ? 1u : 0u);
                         if (PRECISE) {
                             // A_lo * W_hi accumulates into the acc_lo columns that the UMMA above just wrote (in-order pipe)
-                            const uint64_t alo = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES + A_STAGE_BYTES));
+                            const uint64_t alo = umma_desc_kmajor_sw128(a_addr + A_STAGE_BYTES);
                             umma_f16(d_tmem + (uint32_t)BLOCK_N, alo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, 1u);
                         }
+                    }
                     }
                     umma_commit(&empty_bar[stage]);           // frees the smem slot once these MMAs have read it
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -394,12 +432,12 @@ static ConvProfile g_prof;
 static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 static int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
 
-template <int BLOCK_N, bool PRECISE>
+template <int BLOCK_N, bool PRECISE, int HALO = 0>
 static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvKParams& kp, int sms, cudaStream_t st) {
-    using Cfg = ConvCfg<BLOCK_N, PRECISE>;
+    using Cfg = ConvCfg<BLOCK_N, PRECISE, HALO>;
     static bool attr_set = false;
     if (!attr_set) {
-        int rc = check_cuda(cudaFuncSetAttribute(conv_gemm_f16<BLOCK_N, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES),
+        int rc = check_cuda(cudaFuncSetAttribute(conv_gemm_f16<BLOCK_N, PRECISE, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES),
                             "cudaFuncSetAttribute(conv_gemm_f16)");
         if (rc) return rc;
         attr_set = true;
@@ -409,7 +447,7 @@ static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
     const bool prof = g_prof.enabled && g_prof.used + 2 <= g_prof.ev.size();
     if (g_prof.enabled && !prof) ++g_prof.dropped;
     if (prof) cudaEventRecord(g_prof.ev[g_prof.used], st);
-    conv_gemm_f16<BLOCK_N, PRECISE><<<grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b, kp);
+    conv_gemm_f16<BLOCK_N, PRECISE, HALO><<<grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b, kp);
     if (prof) {
         cudaEventRecord(g_prof.ev[g_prof.used + 1], st);
         g_prof.used += 2;
@@ -459,18 +497,29 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     kp.lo0 = d->lo0; kp.lo1 = d->lo1;
     kp.up2x = d->up2x ? 1 : 0;
     kp.out_f32 = d->out_f32 ? 1 : 0;
-    {   // K stages (64 elements each) per in-TMEM accumulation chain; env NBP_CONV_KCHUNK overrides (0 = unbounded)
-        static int kchunk_env = -1;
-        if (kchunk_env < 0) { const char* e = getenv("NBP_CONV_KCHUNK"); kchunk_env = e ? atoi(e) : 8; }
-        const int total = d->taps * (kp.kc0 + kp.kc1);
-        const int want = d->k_chunk > 0 ? d->k_chunk : kchunk_env;
-        kp.kchunk = (want <= 0 || !precise) ? total : want;
+    // ---- vertical halo reuse (64- and 32-channel tiles, whose K steps are too short to hide the operand latency): tiles inside one
+    // image whose rows are whole 8-pixel swizzle groups; training's short accumulation chains (k_chunk 1..2) keep the plain path
+    static int halo_env = -1, kchunk_env = -1;
+    if (halo_env < 0) { const char* e = getenv("NBP_CONV_HALO"); halo_env = e ? atoi(e) : 1; }
+    if (kchunk_env < 0) { const char* e = getenv("NBP_CONV_KCHUNK"); kchunk_env = e ? atoi(e) : 8; }
+    const int want = d->k_chunk > 0 ? d->k_chunk : kchunk_env;       // K slices (64 elements each) per in-TMEM accumulation chain; 0 = unbounded
+    const bool halo = halo_env && precise && block_n <= 64 && (d->taps == 9 || d->up2x) && kp.tn == 1 && kp.tw >= 8 &&
+                      (kp.th + 2) * kp.tw <= HALO_ROWS && !(want > 0 && want < 3);
+    const int planes_ = precise ? 2 : 1;
+    kp.gtaps = halo ? (d->up2x ? 2 : 3) : 1;
+    kp.ngroups = halo ? (d->up2x ? 2 : 3) : d->taps;
+    kp.a_tx = planes_ * (halo ? kp.th + 2 : kp.th) * kp.tw * kp.tn * BLOCK_K * 2;
+    kp.aoff_step = kp.tw * BLOCK_K * 2;
+    {   // kp.kchunk = STAGES per accumulation chain (a halo stage carries gtaps K slices)
+        const int total = kp.ngroups * (kp.kc0 + kp.kc1);
+        int want_st = want <= 0 ? total : (want + kp.gtaps - 1) / kp.gtaps;
+        kp.kchunk = !precise ? total : want_st;
         if (kp.kchunk > total) kp.kchunk = total;
         if (kp.kchunk < 1) kp.kchunk = 1;
         // A chain only slightly longer than the target (K = 9 slices of a 64-channel 3x3 layer vs 8) stays single: cutting it as
         // 8 + 1 makes the epilogue warps fold two chunks per tile for nothing (measured -3..-13 % on those layers); spreading
         // longer reductions evenly (18 as 6+6+6 instead of 8+8+2) was measured slower and is not done.
-        if (precise && want > 0 && total > kp.kchunk && total <= want + want / 4) kp.kchunk = total;
+        if (precise && want > 0 && total > kp.kchunk && total * kp.gtaps <= want + want / 4) kp.kchunk = total;
     }
     kp.b_rows_per_parity = (precise ? 2 : 1) * d->c_out;
     kp.scale = d->scale; kp.shift = d->shift; kp.relu = d->relu;
@@ -478,9 +527,10 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     if (kp.tn > 256 || kp.th > 256) return invalid("nbp_conv_fwd: image too small for a 128-pixel tile (w=%d h=%d)", d->w, d->h);
 
     CUtensorMap a0, a1, b;
-    int rc = make_act_map(&a0, d->src0, span0, d->ld0, d->n, d->h, d->w, kp.tw, kp.th, kp.tn);
+    const int box_rows = halo ? kp.th + 2 : kp.th;
+    int rc = make_act_map(&a0, d->src0, span0, d->ld0, d->n, d->h, d->w, kp.tw, box_rows, kp.tn);
     if (rc) return rc;
-    if (d->c1 > 0) rc = make_act_map(&a1, d->src1, span1, d->ld1, d->n, d->h, d->w, kp.tw, kp.th, kp.tn);
+    if (d->c1 > 0) rc = make_act_map(&a1, d->src1, span1, d->ld1, d->n, d->h, d->w, kp.tw, box_rows, kp.tn);
     else a1 = a0;
     if (rc) return rc;
     // weights: fast [c_out][K]; precise [(c_out/block_n) tiles][W_hi rows ; W_lo rows][K]
@@ -500,8 +550,10 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     if (precise) {
         switch (block_n) {
             case 128: return launch_conv<128, true>(a0, a1, b, kp, sms, st);
-            case 64:  return launch_conv<64, true>(a0, a1, b, kp, sms, st);
-            default:  return launch_conv<32, true>(a0, a1, b, kp, sms, st);
+            case 64:  return !halo ? launch_conv<64, true>(a0, a1, b, kp, sms, st)
+                             : d->up2x ? launch_conv<64, true, 2>(a0, a1, b, kp, sms, st) : launch_conv<64, true, 3>(a0, a1, b, kp, sms, st);
+            default:  return !halo ? launch_conv<32, true>(a0, a1, b, kp, sms, st)
+                             : d->up2x ? launch_conv<32, true, 2>(a0, a1, b, kp, sms, st) : launch_conv<32, true, 3>(a0, a1, b, kp, sms, st);
         }
     }
     switch (block_n) {
