@@ -281,6 +281,18 @@ int nbp_coverage_percentage(const float* cloud, int64_t cloud_stride, const int3
                             int64_t total_gt, float cell, float threshold, int weight, uint64_t seed, uint8_t* covered,
                             float* coverage, int32_t* counts, void* stream);
 
+/* ------------------------------------------------------------------------------------------ SURVEY section 8(f) row 3
+ * Batched Trimesh-free collision tests of the planner: line_segment_mesh_intersection (macarons/utility/macarons_utils.py:120-151;
+ * callers next_best_path/utility/long_term_utils.py:347, next_best_path/testers/nbp_planning.py:142,245) and the axis rays of
+ * check_camera_in_mesh (long_term_utils.py:158-170).  Meshes packed as for nbp_raster_depth_batched (scene-local face indices).
+ * segments [n][6] fp32: rays == 0: (start, end) -> hit[i] = 1 iff some triangle is crossed at a distance < |end - start| from the
+ * start; rays != 0: (origin, unit direction) -> hit / count over the whole forward ray.  count (may be NULL) = number of triangles
+ * hit (the inside test takes its parity); hit may be NULL when only counts are wanted.  fp64 plane + barycentric formulation
+ * (tolerances as Trimesh's ray_triangle: 1e-13 on the barycentrics, -1e-6 on the forward distance). */
+int nbp_segments_hit_mesh(const float* verts, const int32_t* faces, const int64_t* vert_offsets, const int64_t* face_offsets,
+                          int n_scenes, const float* segments, const int32_t* seg_scene, int n_segments, int rays,
+                          uint8_t* hit, int32_t* count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

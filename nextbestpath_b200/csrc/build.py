@@ -18,6 +18,7 @@ SOURCES = {
     "scatter.cu": ["-fmad=false"],
     "planner.cu": ["-fmad=false"],
     "coverage.cu": ["-fmad=false"],
+    "collision.cu": ["-fmad=false"],
     "conv_tc.cu": [],
     "nn_kernels.cu": [],
     "train_kernels.cu": [],

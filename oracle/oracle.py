@@ -360,3 +360,57 @@ def coverage_percentage(gt, pc, threshold: float = 1.0, weight: int = 2, indices
         flags[a:a + step] = (d2 < thr2).any(axis=1)
     cov = float(np.float32(flags.sum()) / np.float32(len(g))) if len(g) else 0.0
     return (cov, flags) if return_flags else cov
+
+
+# --------------------------------------------------------------------------- section 8f row 3: collision rays
+def _dot3(a, b):
+    return (a[..., 0] * b[..., 0] + a[..., 1] * b[..., 1]) + a[..., 2] * b[..., 2]
+
+
+def _cross3(a, b):
+    return np.stack((a[..., 1] * b[..., 2] - a[..., 2] * b[..., 1], a[..., 2] * b[..., 0] - a[..., 0] * b[..., 2],
+                     a[..., 0] * b[..., 1] - a[..., 1] * b[..., 0]), axis=-1)
+
+
+def segment_mesh_hits(verts, faces, segments, rays: bool = False):
+    """line_segment_mesh_intersection macarons/utility/macarons_utils.py:120-151 (rays=False: segments (n,6) = start, end; returns
+    (hit (n,) bool, count (n,) int)) and the ray casts of check_camera_in_mesh next_best_path/utility/long_term_utils.py:158-170
+    (rays=True: (origin, unit direction)).  The reference delegates to ``trimesh.ray.intersects_location`` (trimesh 4.1.2, not
+    in the tree, not installable here: PARITY UNPINNED).  This restates Trimesh's published ray_triangle formulation in float64:
+    plane intersection, barycentric coordinates by Cramer's rule, accept when all barycentrics lie in [-1e-13, 1+1e-13] and the hit
+    is forward of the origin (distance > -1e-6); a segment keeps hits with |location - start| < |end - start| (:143-144).
+    Every operation is an explicit elementwise float64 op in a fixed order: csrc/collision.cu reproduces it bit for bit."""
+    v = np.asarray(verts, dtype=np.float32).astype(np.float64)
+    tri = v[np.asarray(faces, dtype=np.int64)]                                   # (F, 3, 3)
+    seg = np.asarray(segments, dtype=np.float32).astype(np.float64).reshape(-1, 6)
+    v0, e1, e2 = tri[:, 0], tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]
+    n = _cross3(e1, e2)
+    nn = _dot3(n, n)
+    d00, d01, d11 = _dot3(e1, e1), _dot3(e1, e2), _dot3(e2, e2)
+    hit = np.zeros(len(seg), dtype=bool); count = np.zeros(len(seg), dtype=np.int64)
+    for i, s in enumerate(seg):
+        o, d = s[:3], s[3:]
+        length = 0.0
+        if not rays:
+            d = d - o
+            length = np.sqrt(_dot3(d, d))
+            d = d / length
+        with np.errstate(divide="ignore", invalid="ignore"):
+            denom = _dot3(n, d[None, :])
+            ok = (nn > 0.0) & (np.abs(denom) > 1e-13 * np.sqrt(nn))
+            t = _dot3(n, v0 - o[None, :]) / denom
+            ok &= t > -1e-6
+            p = o[None, :] + t[:, None] * d[None, :]
+            w = p - v0
+            d20, d21 = _dot3(w, e1), _dot3(w, e2)
+            inv = 1.0 / (d00 * d11 - d01 * d01)
+            b1 = (d11 * d20 - d01 * d21) * inv
+            b2 = (d00 * d21 - d01 * d20) * inv
+            b0 = (1.0 - b1) - b2
+            lo, hi = -1e-13, 1.0 + 1e-13
+            ok &= (b0 > lo) & (b1 > lo) & (b2 > lo) & (b0 < hi) & (b1 < hi) & (b2 < hi)
+            if not rays:
+                dl = p - o[None, :]
+                ok &= np.sqrt(_dot3(dl, dl)) < length
+        count[i] = int(ok.sum()); hit[i] = bool(ok.any())
+    return hit, count
