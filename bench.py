@@ -372,7 +372,7 @@ def main():
     ap.add_argument("--prefill", type=int, default=50)
     ap.add_argument("--chunk", type=int, default=32)
     ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "fp16"])
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
