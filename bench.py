@@ -344,7 +344,8 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f16x2 (split-fp16 operands, fp32 accumulate; fp32-grade results)" if args.precision == "fp16x2" else "f16 (fp32 accumulate)",
             "data": "synthetic",
-            "config": {"workload": f"{B_total} parallel AiMDoom-{args.level}-shaped scenes, {S}x{S} grid, inference rollout (BASELINE configs[1])",
+            "config": {"workload": f"{B_total} parallel AiMDoom-{args.level}-shaped scenes, {S}x{S} grid, inference rollout "
+                                   f"(BASELINE configs[{3 if (args.level == 'insane' and S == 512) else 1}])",
                        "scenes_total": B_total, "scenes_per_gpu": per, "image": "256x456", "mesh_level": args.level,
                        "mean_faces_per_scene": float(np.mean([s.n_faces for s in scenes])), "prefill_pose": args.prefill,
                        "mean_cloud_points_per_scene_at_start": cloud_pts, "nbp_chunk": args.chunk, "precision": args.precision,
