@@ -1,3 +1,5 @@
+"""Per-micro-batch timing and allocator statistics of the NBP training step (the probe that found the tape reference cycles,
+profiles/r01_train_bench.txt): python scripts/train_step_probe.py [micro_batch]."""
 import sys, os, time, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nextbestpath_b200.networks import NBP
