@@ -186,6 +186,9 @@ int nbp_conv1x1_head(const void* src, int c_in, int ld_src, int lo_src, const fl
  * torch.nn.BatchNorm2d as instantiated at nbp_model.py:12,15,28,41,46,51) and the backward pass of NBP.forward
  * (autograd through nbp_model.py:110-160, driven by next_best_path/utility/nbp_utils.py:378-390).
  * Forward activations: NHWC fp16x2 split tensors (ld, lo as above).  Gradients between layers: plain NHWC fp32.
+ * The raw pre-BatchNorm tensor `z` of nbp_bn_train_stats / nbp_affine_act / nbp_att_pre / nbp_bn_bwd[_split] (and the destination of
+ * nbp_conv_first) may instead be PLAIN FP32 NHWC: pass lo < 0 and ld = row stride in floats (train mode uses this: the
+ * cancellation in z - mean needs fp32's 24 bits, see scripts/gradient_study.py).
  * `workspace` arguments are caller-owned fp64 scratch of the stated length; they are zeroed by the call. */
 int nbp_bn_train_stats(const void* z, int ld, int lo, int64_t npix, int C, const float* gamma, const float* beta,
                        float* running_mean, float* running_var, float momentum, float eps,

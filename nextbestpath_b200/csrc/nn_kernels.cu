@@ -93,7 +93,12 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) { f[j] = fmaf(acc[8 * c8 + j], s_sc[8 * c8 + j], s_sh[8 * c8 + j]); if (relu) f[j] = fmaxf(f[j], 0.0f); }
-            store8(o + 8 * c8, dst_lo, f);
+            if (dst_lo < 0) {                     // plain fp32 destination (train mode: the raw pre-BatchNorm tensor), row stride dst_ld floats
+                float4* of = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + pix * dst_ld + 8 * c8);
+                of[0] = make_float4(f[0], f[1], f[2], f[3]); of[1] = make_float4(f[4], f[5], f[6], f[7]);
+            } else {
+                store8(o + 8 * c8, dst_lo, f);
+            }
         }
     }
 }
@@ -234,7 +239,8 @@ extern "C" int nbp_conv_first(const float* x, int n, int c_in, int h, int w, con
     if (!x || !weight || !scale || !shift || !dst) return invalid("nbp_conv_first: null pointer argument");
     if (n <= 0 || h <= 0 || w <= 0 || c_in <= 0 || c_in > 16) return invalid("nbp_conv_first: bad sizes n=%d c_in=%d h=%d w=%d", n, c_in, h, w);
     if (c_out != 64) return invalid("nbp_conv_first: c_out must be 64 (got %d)", c_out);
-    int rc = check_plane("nbp_conv_first", c_out, dst_ld, dst_lo);
+    int rc = dst_lo < 0 ? ((dst_ld < c_out || dst_ld % 4) ? invalid("nbp_conv_first: bad fp32 destination stride %d", dst_ld) : NBP_OK)
+                        : check_plane("nbp_conv_first", c_out, dst_ld, dst_lo);
     if (rc) return rc;
     if ((uintptr_t)dst & 15) return invalid("nbp_conv_first: dst must be 16-byte aligned");
     const size_t smem = sizeof(float) * (size_t)(9 * c_in * 64 + 128);

@@ -48,6 +48,16 @@ __device__ __forceinline__ void st8(__half* p, int lo, const float* f) {
     if (lo) *reinterpret_cast<uint4*>(p + lo) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }
 
+__device__ __forceinline__ void ld8f(const float* p, float* f);
+// The raw conv output z feeds BatchNorm (statistics, normalisation, backward).  It is stored either as a split fp16x2 tensor
+// (lo >= 0) or -- train mode, same 4 bytes per element -- as plain fp32 (lo < 0, row stride ld floats): with 22 significant bits
+// the cancellation in (z - mean) flips ReLU / max-pool decisions that the fp32 reference takes the other way, which is what
+// dominated the whole-network gradient error (scripts/gradient_study.py).
+__device__ __forceinline__ void ldz(const __half* z, size_t pix, int ld, int lo, int g, float* f) {
+    if (lo < 0) ld8f(reinterpret_cast<const float*>(z) + pix * (size_t)ld + 8 * g, f);
+    else ld8(z + pix * (size_t)ld + 8 * g, lo, f);
+}
+
 __device__ __forceinline__ void ld8f(const float* p, float* f) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
@@ -92,7 +102,7 @@ __device__ __forceinline__ void channel_reduce(size_t npix, int C, double* out /
 __global__ void __launch_bounds__(256) bn_sum_kernel(const __half* __restrict__ z, int ld, int lo, size_t npix, int C, double* acc) {
     channel_reduce<1>(npix, C, acc, [&](size_t p, int g, float (*a)[8]) {
         float f[8];
-        ld8(z + p * ld + 8 * g, lo, f);
+        ldz(z, p, ld, lo, g, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[0][j] += f[j];
     });
@@ -102,7 +112,7 @@ __global__ void __launch_bounds__(256) bn_sqdev_kernel(const __half* __restrict_
     const double inv = 1.0 / (double)npix;
     channel_reduce<1>(npix, C, acc + C, [&](size_t p, int g, float (*a)[8]) {
         float f[8];
-        ld8(z + p * ld + 8 * g, lo, f);
+        ldz(z, p, ld, lo, g, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float d = f[j] - (float)(acc[8 * g + j] * inv); a[0][j] = fmaf(d, d, a[0][j]); }
     });
@@ -135,7 +145,7 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const __half* __restric
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t p = i / G; const int g = (int)(i - p * G);
         float f[8];
-        ld8(z + p * ld_z + 8 * g, lo_z, f);
+        ldz(z, p, ld_z, lo_z, g, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { f[j] = fmaf(f[j], scale[8 * g + j], shift[8 * g + j]); if (relu) f[j] = fmaxf(f[j], 0.0f); }
         st8(y + p * ld_y + 8 * g, lo_y, f);
@@ -151,7 +161,7 @@ __global__ void __launch_bounds__(256) att_pre_kernel(const __half* __restrict__
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t p = i / G; const int g = (int)(i - p * G);
         float u[8], v[8];
-        ld8(zg + p * ld + 8 * g, lo, u); ld8(zx + p * ld + 8 * g, lo, v);
+        ldz(zg, p, ld, lo, g, u); ldz(zx, p, ld, lo, g, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) u[j] = fmaxf(fmaf(u[j], sg[8 * g + j], tg[8 * g + j]) + fmaf(v[j], sx[8 * g + j], tx[8 * g + j]), 0.0f);
         st8(a + p * ld_a + 8 * g, lo_a, u);
@@ -232,7 +242,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
     __syncthreads();
     channel_reduce<2>(npix, C, acc, [&](size_t p, int g, float (*a)[8]) {
         float f[8], d[8], co[4][8];
-        ld8(z + p * ld_z + 8 * g, lo_z, f);
+        ldz(z, p, ld_z, lo_z, g, f);
         ld8f(dy + p * ld_dy + 8 * g, d);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -301,7 +311,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t p = i / G; const int g = (int)(i - p * G);
         float f[8], d[8], o[8], co[7][8];
-        ld8(z + p * ld_z + 8 * g, lo_z, f);
+        ldz(z, p, ld_z, lo_z, g, f);
         ld8f(dy + p * ld_dy + 8 * g, d);
 #pragma unroll
         for (int q = 0; q < 7; ++q) {

@@ -82,13 +82,31 @@ def _packed(t, key, make):
     return w
 
 
+class _ZF32:
+    """The raw pre-BatchNorm tensor z as plain fp32 NHWC (same 4 bytes per element as the split fp16x2 format).  BatchNorm subtracts
+    the batch mean from z: with the 22 significant bits of fp16x2 that cancellation flips ReLU / max-pool decisions the fp32
+    reference takes the other way, and those flips -- not the GEMM precision -- dominated the whole-network gradient error
+    (scripts/gradient_study.py: 4.2e-3 -> 5.5e-5 at B=2, S=128).  The kernels take it through the `lo < 0` convention."""
+
+    __slots__ = ("t", "c", "ld", "lo", "h", "w")
+
+    def __init__(self, dev, B, h, w, c):
+        self.t = torch.empty((B, h, w, c), dtype=torch.float32, device=dev)
+        self.c, self.ld, self.lo, self.h, self.w = c, c, -1, h, w
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+
 def _raw_conv(t, name, w, bias, src, taps, dst):
-    """dst = conv(src) + bias (no normalisation): the raw pre-BatchNorm tensor z."""
-    pk = {"precise": True}
-    layer = {"w": _packed(t, ("fwd", name), lambda: M._pack_gemm_weight(_w2d(w), True)), "scale": torch.ones_like(bias),
-             "shift": bias.contiguous(), "c_out": w.shape[0]}
-    M._conv(pk, layer, t.B, src, taps, dst, relu=False, k_chunk=TRAIN_K_CHUNK)
-    return layer
+    """dst (_ZF32) = conv(src) + bias (no normalisation): the raw pre-BatchNorm tensor z, fp32 epilogue of the tcgen05 kernel."""
+    cout = w.shape[0]
+    wp = _packed(t, ("fwd", name), lambda: M._pack_gemm_weight(_w2d(w), True))
+    ones = _packed(t, ("ones", cout), lambda: torch.ones(cout, dtype=torch.float32, device=t.dev))
+    d = _lib.ConvDesc(1, src.ptr, src.c, src.ld, src.lo, None, 0, 0, 0, t.B, src.h, src.w, taps, 0, wp.data_ptr(), cout,
+                      ones.data_ptr(), bias.contiguous().data_ptr(), 0, dst.ptr, dst.ld, 0, 0, 1, TRAIN_K_CHUNK)
+    _chk(t.L.nbp_conv_fwd(ctypes.byref(d), _st()), "nbp_conv_fwd(raw z)")
 
 
 def _bn_stats(t, z, npix, bn):
@@ -171,7 +189,7 @@ def _cbr(t, sd, conv, bn, src, taps=9, dst=None, relu=True):
     bnp = {k: sd[f"{bn}.{k}"] for k in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")}
     cout = w.shape[0]
     npix = t.B * src.h * src.w
-    z = t.new(src.h, src.w, cout)
+    z = _ZF32(t.dev, t.B, src.h, src.w, cout)
     _raw_conv(t, conv, w, b, src, taps, z)
     stats = _bn_stats(t, z, npix, bnp)
     y = dst if dst is not None else t.new(src.h, src.w, cout)
@@ -199,7 +217,7 @@ def forward_train(sd, x, cache=None):
     # ---- stem: Conv1.conv.0 (CUDA cores) raw + bias, then BN + ReLU
     w0, b0 = sd["Conv1.conv.0.weight"], sd["Conv1.conv.0.bias"]
     bn0 = {k: sd[f"Conv1.conv.1.{k}"] for k in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")}
-    z0 = t.new(S, S2, 64)
+    z0 = _ZF32(dev, B, S, S2, 64)
     w0p = w0.permute(2, 3, 1, 0).reshape(-1, 64).contiguous()
     ones64 = torch.ones(64, device=dev)
     _chk(L.nbp_conv_first(x.data_ptr(), B, cin0, S, S2, w0p.data_ptr(), ones64.data_ptr(), b0.contiguous().data_ptr(), 64, 0,
@@ -247,7 +265,7 @@ def forward_train(sd, x, cache=None):
         wg, bg = sd[f"Att{tg}.W_g.0.weight"], sd[f"Att{tg}.W_g.0.bias"]
         wx, bx = sd[f"Att{tg}.W_x.0.weight"], sd[f"Att{tg}.W_x.0.bias"]
         f_int = wg.shape[0]
-        zg, zx = t.new(h2, w2, f_int), t.new(h2, w2, f_int)
+        zg, zx = _ZF32(dev, B, h2, w2, f_int), _ZF32(dev, B, h2, w2, f_int)
         _raw_conv(t, f"Att{tg}.W_g.0", wg, bg, g, 1, zg)
         _raw_conv(t, f"Att{tg}.W_x.0", wx, bx, skip, 1, zx)
         bng = {k: sd[f"Att{tg}.W_g.1.{k}"] for k in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")}
