@@ -49,6 +49,9 @@ uint64_t nbp_launch_count(void);
  * faces [sumF,3] int32 packed, indices LOCAL to the scene's vertex block.
  * zbuf [n_views,H,W] fp32 view-space z, -1 where no face; pix_to_face [n_views,H,W] int32 scene-local
  * face index or -1 (may be NULL).  total_view_faces = sum over views of the face count of its scene.
+ * Workspace (caller-owned, size from nbp_raster_workspace_bytes): per view up to 2 triangle records (96 B) + pixel boxes (8 B) per
+ * face and 32 coarse-bin lists of 8-byte entries with the same capacity; only the used prefix of each list is touched.  Images whose
+ * coarse bins (<= 32 per view, multiples of 16 px) would exceed 256 px are rejected (NBP_ERR_INVALID).
  */
 size_t nbp_raster_workspace_bytes(int n_views, int64_t total_view_faces);
 int nbp_raster_depth_batched(const float* verts, const int32_t* faces,
