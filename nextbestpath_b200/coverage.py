@@ -91,17 +91,18 @@ def calculate_coverage_percentage(pc1, pc2, threshold=1, weight=2):
     """Drop-in for next_best_path/utility/long_term_utils.py:457-468 (same arguments, returns a Python float): pc1 = ground-truth
     points (N,3), pc2 = reconstruction (M,3), CUDA tensors.  The sub-sampling draws ``torch.randperm(len(pc2))`` from the default
     CPU generator exactly like ``random_sample_pc`` (:436-446), so a seeded run follows the reference's random stream.
-    The grid over pc1 is cached per (storage, length): the drivers pass the same ground-truth tensor every pose."""
+    The grid over pc1 is cached while the drivers pass the SAME tensor object, unmodified (identity + in-place version counter;
+    the cache holds a reference, so the allocator cannot hand its address to another scene's cloud)."""
     if len(pc2) == 0:
         return 0.
     if not (isinstance(pc1, torch.Tensor) and pc1.is_cuda and isinstance(pc2, torch.Tensor) and pc2.is_cuda):
         raise RuntimeError("calculate_coverage_percentage: CUDA tensors only (no CPU fallback)")
-    key = (pc1.data_ptr(), tuple(pc1.shape), float(threshold), str(pc1.device))
-    idx = _index_cache.get(key)
-    if idx is None:
-        _index_cache.clear()
+    ent = _index_cache.get("gt")
+    if ent is not None and ent[0] is pc1 and ent[1] == pc1._version and ent[2] == float(threshold):
+        idx = ent[3]
+    else:
         idx = CoverageIndex([pc1.detach().float()], pc1.device, threshold=float(threshold))
-        _index_cache[key] = idx
+        _index_cache["gt"] = (pc1, pc1._version, float(threshold), idx)
     n2, want = pc2.shape[0], int(len(pc1) * weight)
     sample = None
     if n2 > want:

@@ -41,6 +41,7 @@ class _Tape:
         self.ws = torch.zeros(2 * 2048 + 16, dtype=torch.float64, device=dev)        # fp64 reduction scratch
         self.ws_big = torch.zeros(9 * 16 * 64 + 8 * 256 + 64, dtype=torch.float64, device=dev)
         self.ops = []            # backward closures, run in reverse
+        self.capture = None      # dict: the tensors every discrete decision is taken from (module.capture_decisions, tests)
         self.grads = {}          # id(_Act) -> fp32 NHWC dense gradient [npix, c]
         self.pgrads = {}         # parameter name -> fp32 gradient tensor
 
@@ -195,6 +196,8 @@ def _cbr(t, sd, conv, bn, src, taps=9, dst=None, relu=True):
     y = dst if dst is not None else t.new(src.h, src.w, cout)
     _chk(t.L.nbp_affine_act(z.ptr, z.ld, z.lo, npix, cout, stats[2].data_ptr(), stats[3].data_ptr(), 1 if relu else 0,
                             y.t.data_ptr() + 2 * y.off, y.ld, y.lo, _st()), "nbp_affine_act")
+    if t.capture is not None and relu:
+        t.capture[bn] = ("affine", z.t, stats)
 
     def backward(dy, need_dsrc=True):
         """dy: fp32 [npix, ld_dy] view (first `cout` columns used).  Returns d(src) fp32 [npix, cin]."""
@@ -204,13 +207,15 @@ def _cbr(t, sd, conv, bn, src, taps=9, dst=None, relu=True):
     return y, backward
 
 
-def forward_train(sd, x, cache=None):
+def forward_train(sd, x, cache=None, capture=False):
     """sd: name -> CUDA fp32 tensor (parameters and BatchNorm buffers; buffers are updated in place).
     ``cache``: dict that outlives the call and holds the packed GEMM weights (the caller drops it when parameters change).
     Returns (out1, out2, tape)."""
     dev = x.device
     B, cin0, S, S2 = x.shape
     t = _Tape(dev, B, cache)
+    if capture:
+        t.capture = {}
     L = t.L
     st = _st()
 
@@ -226,6 +231,8 @@ def forward_train(sd, x, cache=None):
     stats0 = _bn_stats(t, z0, npix1, bn0)
     y0 = t.new(S, S2, 64)
     _chk(L.nbp_affine_act(z0.ptr, z0.ld, z0.lo, npix1, 64, stats0[2].data_ptr(), stats0[3].data_ptr(), 1, y0.ptr, y0.ld, y0.lo, st), "nbp_affine_act")
+    if t.capture is not None:
+        t.capture["Conv1.conv.1"] = ("affine", z0.t, stats0)
 
     def stem_backward(dy):
         dz, amax = t.f32(npix1, 64), t.f32(1)
@@ -245,6 +252,8 @@ def forward_train(sd, x, cache=None):
     for lvl in range(2, 6):
         p = t.new(cur.h // 2, cur.w // 2, cur.c)
         _chk(L.nbp_maxpool2x2(cur.ptr, B, cur.h, cur.w, cur.c, cur.ld, cur.lo, p.ptr, p.ld, p.lo, st), "nbp_maxpool2x2")
+        if t.capture is not None:
+            t.capture[f"pool{lvl}"] = ("pool", cur.t, cur.c)
         ya, bw_a = _cbr(t, sd, f"Conv{lvl}.conv.0", f"Conv{lvl}.conv.1", p)
         yb, bw_b = _cbr(t, sd, f"Conv{lvl}.conv.3", f"Conv{lvl}.conv.4", ya)
         enc_bw[lvl] = (bw_b, bw_a, cur, p)
@@ -275,6 +284,8 @@ def forward_train(sd, x, cache=None):
         a = t.new(h2, w2, f_int)
         _chk(L.nbp_att_pre(zg.ptr, zx.ptr, zg.ld, zg.lo, npix, f_int, sg[2].data_ptr(), sg[3].data_ptr(), sx[2].data_ptr(), sx[3].data_ptr(),
                            a.ptr, a.ld, a.lo, st), "nbp_att_pre")
+        if t.capture is not None:
+            t.capture[f"Att{tg}.relu"] = ("act", a.t, f_int)
         w_psi = sd[f"Att{tg}.psi.0.weight"].reshape(-1).contiguous()
         b_psi = sd[f"Att{tg}.psi.0.bias"]
         zpsi, stat4, psi = t.f32(npix), t.f32(4), t.f32(npix)
@@ -376,6 +387,37 @@ def forward_train(sd, x, cache=None):
     return out1, out2, t
 
 
+def decisions_from_capture(capture):
+    """The discrete decisions the backward kernels take, as NCHW tensors keyed like ``oracle.nbp_torch.Decisions``: ReLU masks
+    (bool) and 2x2 max-pool window indices (long, first maximum in window order).  They are recomputed here from the very tensors
+    the kernels read, with the kernels' expressions: ``fmaf(z, scale, shift) > 0`` (bn_bwd_*; evaluated in float64, where the
+    product is exact, so the sign is the fused operation's), ``a > 0`` on the stored fp16x2 value (psi_bwd), and
+    ``v[k] > v[best]`` over the stored fp16x2 values (maxpool_bwd).  Filled when ``module.capture_decisions`` is true; test
+    support for the flip-robust gradient parity test, not used by training itself."""
+    out = {}
+    for name, (kind, t, aux) in capture.items():
+        if kind == "affine":
+            y = t.double() * aux[2].double() + aux[3].double()                     # (B,h,w,C)
+            out[name] = (y > 0).permute(0, 3, 1, 2).contiguous()
+        else:
+            c = aux
+            v = t[..., :c].float() + t[..., c:2 * c].float() / M.LO_SCALE
+            v = v.permute(0, 3, 1, 2)
+            if kind == "act":
+                out[name] = (v > 0).contiguous()
+            else:
+                B, C, H, W = v.shape
+                win = v.reshape(B, C, H // 2, 2, W // 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(B, C, H // 2, W // 2, 4)
+                best = torch.zeros(win.shape[:-1], dtype=torch.long, device=win.device)
+                bv = win[..., 0]
+                for k in range(1, 4):
+                    upd = win[..., k] > bv
+                    best = torch.where(upd, torch.full_like(best, k), best)
+                    bv = torch.where(upd, win[..., k], bv)
+                out[name] = best
+    return out
+
+
 class NBPTrainFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, x, names, *params):
@@ -388,7 +430,10 @@ class NBPTrainFunction(torch.autograd.Function):
         if cache is None or cache.get("key") != key:
             cache = {"key": key}
             module._train_pack = cache
-        out1, out2, tape = forward_train(sd, x.contiguous().float(), cache)
+        out1, out2, tape = forward_train(sd, x.contiguous().float(), cache, capture=bool(getattr(module, "capture_decisions", False)))
+        if tape.capture is not None:
+            module.last_decisions = decisions_from_capture(tape.capture)
+            tape.capture = None
         ctx.tape, ctx.names, ctx.params = tape, names, params
         return out1, out2
 

@@ -97,14 +97,15 @@ class Camera:
     # ---- capture_image (macarons_utils.py:2743-2786)
     def _pack(self, mesh):
         v, f = mesh.verts_list()[0], mesh.faces_list()[0]
-        key = (v.data_ptr(), f.data_ptr(), v.shape[0], f.shape[0])
-        if key != self._mesh_key:
+        # identity + in-place version of the caller's tensors (the key holds references: no address reuse, vertex edits are seen)
+        k0 = self._mesh_key
+        if k0 is None or k0[0] is not v or k0[1] is not f or k0[2] != v._version or k0[3] != f._version:
             dev = self.device
             self._mesh_pack = (v.to(dev, torch.float32).contiguous(), f.to(dev, torch.int32).contiguous(),
                                torch.tensor([0, v.shape[0]], dtype=torch.int64, device=dev),
                                torch.tensor([0, f.shape[0]], dtype=torch.int64, device=dev),
                                torch.zeros(1, dtype=torch.int32, device=dev), [int(f.shape[0])])
-            self._mesh_key = key
+            self._mesh_key = (v, f, v._version, f._version)
         return self._mesh_pack
 
     def capture_image(self, mesh, fov_camera=None, save_frame=True, dir_path=None):

@@ -39,41 +39,95 @@ def _conv(x, sd, prefix, pad):
     return F.conv2d(x, sd[prefix + ".weight"], sd[prefix + ".bias"], stride=1, padding=pad)
 
 
-def _double_conv(x, sd, name, training):
+class Decisions:
+    """The network's discrete decisions (which side of every ReLU an element falls on, which of its four inputs every
+    2x2 max-pool forwards), keyed by the BatchNorm in front of the ReLU ("Conv1.conv.1", "Up5_1.up.2", ...), by
+    "Att{l}_{d}.relu" for the attention gates and by "pool2".."pool5" (the pool feeding encoder level l).
+
+    ``native`` is filled by ``forward`` with the decisions its own arithmetic takes.  If ``forced`` is given, the forward
+    pass takes those decisions instead (ReLU: multiply by the given 0/1 mask, pool: gather the given window index, window
+    order (0,0),(0,1),(1,0),(1,1)), which pins the evaluation to ONE linear piece of the piecewise-linear network: two
+    arithmetics that take the same decisions differ by rounding only.  Test infrastructure for the gradient parity test
+    (tests/test_train_gpu.py): the whole-network gradient is discontinuous across a decision flip, so a comparison is only
+    a precision statement when both sides are on the same piece."""
+
+    def __init__(self, forced=None):
+        self.forced = forced
+        self.native = {}
+
+
+def _relu(x, name, dec):
+    if dec is None:
+        return F.relu(x)
+    dec.native[name] = x.detach() > 0
+    if dec.forced is None:
+        return F.relu(x)
+    return x * dec.forced[name].to(x.dtype)
+
+
+def _windows(x):
+    B, C, H, W = x.shape
+    return x.reshape(B, C, H // 2, 2, W // 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(B, C, H // 2, W // 2, 4)
+
+
+def first_argmax4(win):
+    """Index of the first maximum over the last (window) dimension -- torch.max_pool2d's and the CUDA kernel's tie rule."""
+    best = torch.zeros(win.shape[:-1], dtype=torch.long, device=win.device)
+    bv = win[..., 0]
+    for k in range(1, 4):
+        upd = win[..., k] > bv
+        best = torch.where(upd, torch.full_like(best, k), best)
+        bv = torch.where(upd, win[..., k], bv)
+    return best
+
+
+def _pool(x, name, dec):
+    if dec is None:
+        return F.max_pool2d(x, 2, 2)
+    win = _windows(x)
+    dec.native[name] = first_argmax4(win.detach())
+    idx = dec.native[name] if dec.forced is None else dec.forced[name]
+    return win.gather(-1, idx.unsqueeze(-1)).squeeze(-1)
+
+
+def _double_conv(x, sd, name, training, dec=None):
     """conv_block nbp_model.py:8-21: (3x3 conv + BN + ReLU) x 2 at Sequential indices 0,1 / 3,4."""
-    x = F.relu(_bn(_conv(x, sd, f"{name}.conv.0", 1), sd, f"{name}.conv.1", training))
-    return F.relu(_bn(_conv(x, sd, f"{name}.conv.3", 1), sd, f"{name}.conv.4", training))
+    x = _relu(_bn(_conv(x, sd, f"{name}.conv.0", 1), sd, f"{name}.conv.1", training), f"{name}.conv.1", dec)
+    return _relu(_bn(_conv(x, sd, f"{name}.conv.3", 1), sd, f"{name}.conv.4", training), f"{name}.conv.4", dec)
 
 
-def _up(x, sd, name, training):
+def _up(x, sd, name, training, dec=None):
     """up_conv nbp_model.py:23-34: nearest x2, 3x3 conv, BN, ReLU (Sequential indices 1, 2)."""
     x = F.interpolate(x, scale_factor=2, mode="nearest")
-    return F.relu(_bn(_conv(x, sd, f"{name}.up.1", 1), sd, f"{name}.up.2", training))
+    return _relu(_bn(_conv(x, sd, f"{name}.up.1", 1), sd, f"{name}.up.2", training), f"{name}.up.2", dec)
 
 
-def _gate(g, x, sd, name, training):
+def _gate(g, x, sd, name, training, dec=None):
     """Attention_block nbp_model.py:36-62: x * sigmoid(BN(psi(relu(BN(Wg g) + BN(Wx x)))))."""
     g1 = _bn(_conv(g, sd, f"{name}.W_g.0", 0), sd, f"{name}.W_g.1", training)
     x1 = _bn(_conv(x, sd, f"{name}.W_x.0", 0), sd, f"{name}.W_x.1", training)
-    a = F.relu(g1 + x1)
+    a = _relu(g1 + x1, f"{name}.relu", dec)
     psi = torch.sigmoid(_bn(_conv(a, sd, f"{name}.psi.0", 0), sd, f"{name}.psi.1", training))
     return x * psi
 
 
-def forward(sd, x, training: bool = False):
+def forward(sd, x, training: bool = False, decisions: "Decisions | None" = None):
     """NBP.forward nbp_model.py:110-160. ``sd`` maps the reference's state_dict keys to tensors
-    (parameters may require grad).  Returns (out1 (B,8,S/4,S/4), out2 (B,1,S,S))."""
-    pool = lambda t: F.max_pool2d(t, 2, 2)
-    x1 = _double_conv(x, sd, "Conv1", training)
-    x2 = _double_conv(pool(x1), sd, "Conv2", training)
-    x3 = _double_conv(pool(x2), sd, "Conv3", training)
-    x4 = _double_conv(pool(x3), sd, "Conv4", training)
-    x5 = _double_conv(pool(x4), sd, "Conv5", training)
+    (parameters may require grad).  Returns (out1 (B,8,S/4,S/4), out2 (B,1,S,S)).  ``decisions``: see ``Decisions``
+    (None = the reference's own F.relu / F.max_pool2d calls)."""
+    dec = decisions
+    _dc = _double_conv
+    _double_conv_d = lambda t, s, n, tr: _dc(t, s, n, tr, dec)
+    x1 = _double_conv_d(x, sd, "Conv1", training)
+    x2 = _double_conv_d(_pool(x1, "pool2", dec), sd, "Conv2", training)
+    x3 = _double_conv_d(_pool(x2, "pool3", dec), sd, "Conv3", training)
+    x4 = _double_conv_d(_pool(x3, "pool4", dec), sd, "Conv4", training)
+    x5 = _double_conv_d(_pool(x4, "pool5", dec), sd, "Conv5", training)
 
-    def stage(d, skip, lvl, dec):
-        u = _up(d, sd, f"Up{lvl}_{dec}", training)
-        s = _gate(u, skip, sd, f"Att{lvl}_{dec}", training)
-        return _double_conv(torch.cat((s, u), dim=1), sd, f"Up_conv{lvl}_{dec}", training)
+    def stage(d, skip, lvl, dec_no):
+        u = _up(d, sd, f"Up{lvl}_{dec_no}", training, dec)
+        s = _gate(u, skip, sd, f"Att{lvl}_{dec_no}", training, dec)
+        return _double_conv_d(torch.cat((s, u), dim=1), sd, f"Up_conv{lvl}_{dec_no}", training)
 
     d = stage(x5, x4, 5, 1)
     d = stage(d, x3, 4, 1)

@@ -11,6 +11,8 @@ What is pinned:
   nbp_eval.npz   : next_best_path/networks/nbp_model.py NBP.forward in eval mode (S=128, B=1)
   coverage.npz   : next_best_path/utility/long_term_utils.py calculate_coverage_percentage (:436-468), executed from the reference tree
                    (``--coverage-only`` regenerates just this file)
+  dropin.npz     : the driver lines nbp_planning.py:112-132,166-193 and nbp_utils.py:340-391 executed from the reference tree with the
+                   reference's own functions bound (``--dropin-only`` regenerates just this file)
   nbp_train.npz  : NBP.forward (train mode) + NBP.loss + backward: loss, per-parameter gradient norms,
                    BN running statistics after the step (S=64, B=2)
 """
@@ -128,6 +130,73 @@ def coverage_golden():
     print("coverage.npz:", {k: float(v) for k, v in out.items() if k.endswith("_cov")})
 
 
+def dropin_golden(NBP, ru):
+    """dropin.npz: the reference's OWN driver lines, executed from /root/reference and bound to the reference's OWN CPU functions
+    (next_best_path/testers/nbp_planning.py:112-132,166-193 and next_best_path/utility/nbp_utils.py:340-391).  The GPU test binds
+    the CUDA shims into the same call pattern (oracle/driver_lines.py, pinned to these lines by tests/test_dropin_lines.py)."""
+    import random
+    import types as _types
+    from oracle import driver_lines as DL
+    from oracle import nbp_torch as O
+    out = {}
+    # ---- planning lines
+    pc, traj, pose, y_bins = DL.demo_pose_inputs()
+    net = NBP(); net.load_state_dict(O.golden_state_dict(seed=9)); net.eval()
+    raw = {}
+
+    def nbp(x):
+        with torch.no_grad():
+            raw["v"], raw["o"] = net(x)
+        return raw["v"], raw["o"].clone()
+
+    ns = planning_namespace(ru, pc, traj, pose, y_bins, nbp, "cpu", (256, 256))
+    exec_planning_lines(ns)
+    out["model_input_idx"], out["model_input_val"] = sparse(torch.cat((ns["current_pc_imgs"], ns["current_previous_trajectory_img"]), 1).numpy())
+    out["value_map"] = raw["v"].numpy(); out["raw_obstacle_map"] = raw["o"].numpy()
+    out["fused"] = np.packbits(ns["predicted_obstacle_map"].numpy().astype(np.uint8))
+    out["full_proj"] = np.packbits(ns["full_pc_projection"].numpy().astype(np.uint8))
+    out["max_gain_map"] = ns["max_gain_map"].numpy()
+    # ---- training lines
+    recs = DL.demo_replay_records()
+    net = NBP(); net.load_state_dict(O.golden_state_dict(seed=9)); net.train()
+    opt = DL.RecordingAdamW(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    fn = exec_train_lines()
+    random.seed(8)
+    losses = fn(recs, _types.SimpleNamespace(nbp_batch_size=2), opt, net, "cpu", 2)
+    out["train_losses"] = np.array(losses, dtype=np.float64)
+    out["train_grad_names"] = np.array([n for n, _ in net.named_parameters()])
+    out["train_grad_norms"] = np.array([float(g.double().norm()) for g in opt.recorded])
+    out["train_rm_conv1"] = net.state_dict()["Conv1.conv.1.running_mean"].numpy()
+    np.savez_compressed(os.path.join(HERE, "dropin.npz"), **out)
+    print("dropin.npz: losses", losses, "fused ones", int(ns["predicted_obstacle_map"].sum()), "input points", float(out["model_input_val"].sum()))
+
+
+def planning_namespace(ru, pc, traj, pose, y_bins, nbp, device, size):
+    import types as _types
+    return {"torch": torch, "device": device, "pc2img_size": size, "prediction_range": (-40, 40), "n_pieces": 4,
+            "transform_points_to_n_pieces": ru.transform_points_to_n_pieces, "map_points_to_n_imgs": ru.map_points_to_n_imgs,
+            "full_pc": pc.to(device), "y_bins": y_bins.to(device), "camera_current_pose": pose.to(device),
+            "camera": _types.SimpleNamespace(X_cam_history=traj.to(device)), "nbp": nbp}
+
+
+def exec_planning_lines(ns, root="/root/reference"):
+    """nbp_planning.py:112-132 then :166-193, run from where they lie."""
+    path = os.path.join(root, "next_best_path/testers/nbp_planning.py")
+    exec(_ref_lines(path, "bins = torch.bucketize(full_pc[:, 1]", "current_previous_trajectory_img = previous_trajectory_img.unsqueeze(0)"), ns)
+    exec(_ref_lines(path, "predicted_value_map, predicted_obstacle_map = nbp(", "max_gain_map, _ = torch.max("), ns)
+    return ns
+
+
+def exec_train_lines(root="/root/reference", grad_scaler=None):
+    """def train_experience_data (nbp_utils.py:340-391), defined from the reference's own source text."""
+    import random
+    if grad_scaler is None:
+        from torch.cuda.amp import GradScaler as grad_scaler                 # the reference's import (nbp_utils.py:14)
+    ns = {"torch": torch, "np": np, "random": random, "GradScaler": grad_scaler}
+    exec(_ref_lines(os.path.join(root, "next_best_path/utility/nbp_utils.py"), "def train_experience_data(", "return training_loss"), ns)
+    return ns["train_experience_data"]
+
+
 def main():
     NBP, ru = import_reference()
     from oracle import nbp_torch as O
@@ -205,10 +274,15 @@ def main():
                         **{"probe_" + k.replace(".", "_"): v for k, v in probe.items()})
     planner_golden(ru)
     coverage_golden()
+    dropin_golden(NBP, ru)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
 
+
+if __name__ == "__main__" and "--dropin-only" in sys.argv:
+    dropin_golden(*import_reference())
+    sys.exit(0)
 
 if __name__ == "__main__" and "--coverage-only" in sys.argv:
     coverage_golden()

@@ -107,6 +107,24 @@ def test_cuda_coverage_dropin_follows_reference_random_stream():
 
 
 @pytest.mark.gpu
+def test_cuda_coverage_dropin_cache_is_not_keyed_on_the_address():
+    """A new ground-truth cloud of the same shape -- possibly at the address the allocator just recycled -- or an in-place
+    edit of the cached one must rebuild the index (the cache used to be keyed on data_ptr + shape)."""
+    from nextbestpath_b200.coverage import calculate_coverage_percentage
+    dev = "cuda:0"
+    pc = torch.from_numpy(GOLD["all_pc"]).to(dev)
+    gt_a = torch.from_numpy(GOLD["gt"]).to(dev)
+    a = calculate_coverage_percentage(gt_a, pc)
+    ptr = gt_a.data_ptr()
+    del gt_a
+    gt_b = torch.from_numpy(GOLD["gt"] + np.array([500.0, 0.0, 0.0], np.float32)).to(dev)      # far away: nothing is covered
+    b = calculate_coverage_percentage(gt_b, pc)
+    assert a > 0.05 and b == 0.0, (a, b, gt_b.data_ptr() == ptr)
+    gt_b -= torch.tensor([500.0, 0.0, 0.0], device=dev)                                          # in-place edit of the cached tensor
+    assert calculate_coverage_percentage(gt_b, pc) == a
+
+
+@pytest.mark.gpu
 def test_cuda_coverage_keyed_sample_is_a_uniform_subset():
     from nextbestpath_b200.coverage import CoverageIndex
     dev = "cuda:0"

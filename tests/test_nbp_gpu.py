@@ -229,9 +229,9 @@ def _errs(a, b):
     return ((a - b).abs().max() / b.abs().max()).item(), ((a - b).norm() / b.norm()).item(), (a - b).abs().mean().item()
 
 
-@pytest.mark.parametrize("B,S", [(1, 128), (3, 64), (2, 256)])
+@pytest.mark.parametrize("B,S", [(1, 128), (3, 64), (2, 256), (1, 512)])
 def test_nbp_forward_matches_fp32_oracle(B, S):
-    """The parity path (precision "fp16x2").  config[0] of BASELINE.json is (B=1, S=128)."""
+    """The parity path (precision "fp16x2").  config[0] of BASELINE.json is (B=1, S=128), configs[3] runs the 512x512 grid."""
     sd = NT.golden_state_dict(seed=9)
     net = NBP()
     net.load_state_dict(sd)

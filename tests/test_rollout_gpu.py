@@ -16,7 +16,7 @@ DEV = "cuda:0"
 H, W, S = 48, 86, 64
 
 
-def _oracle_rollout(scene, poses, az, n_steps, sd, gf, sensor_range):
+def _oracle_rollout(scene, poses, az, n_steps, sd, gf, sensor_range, S=S, H=H, W=W):
     """The reference loop (nbp_planning.py:60-355) restricted to the scoped stages, one scene, CPU."""
     verts, faces = scene.verts, scene.faces
     bounds = O.y_bins_from_verts(torch.from_numpy(verts)).numpy()[:-1]
@@ -61,9 +61,10 @@ def test_product_camera_rt_equals_oracle():
             assert torch.equal(mine[k - 1, b], torch.cat((X_, V_)))
 
 
-def test_rollout_matches_oracle_rollout():
-    n_steps, B = 3, 3
-    scenes = [syn.make_scene(40 + i, tri_budget=600 + 400 * i) for i in range(B)]
+@pytest.mark.parametrize("n_steps,B,S,H,W,tris", [(3, 3, 64, 48, 86, 600), (1, 2, 512, 64, 114, 6000)])
+def test_rollout_matches_oracle_rollout(n_steps, B, S, H, W, tris):
+    """Second case: BASELINE configs[3]-shaped step (512x512 grid, larger meshes; image reduced so the CPU oracle finishes)."""
+    scenes = [syn.make_scene(40 + i, tri_budget=tris + 400 * i) for i in range(B)]
     walks = [syn.random_walk(sc, n_steps + 1, seed=70 + i) for i, sc in enumerate(scenes)]
     poses = np.stack([w[0] for w in walks])          # (B, n_steps+1, 5)
     az = np.stack([w[1] for w in walks])
@@ -80,7 +81,7 @@ def test_rollout_matches_oracle_rollout():
     assert eng.overflow.item() == 0
     lens = eng.cloud_len.cpu().numpy()
     for b in range(B):
-        grids, outs, cloud = _oracle_rollout(scenes[b], poses[b], az[b], n_steps, sd, 1.0, 30.0)
+        grids, outs, cloud = _oracle_rollout(scenes[b], poses[b], az[b], n_steps, sd, 1.0, 30.0, S, H, W)
         assert lens[b] == len(cloud)
         assert np.array_equal(eng.cloud[b, : lens[b]].cpu().numpy(), cloud)            # same points, same order
         for t in range(n_steps):
@@ -89,11 +90,12 @@ def test_rollout_matches_oracle_rollout():
             e1 = (got[t][1][b] - o1).abs().max() / o1.abs().max()
             e2 = (got[t][2][b] - o2).abs().max()
             l2 = (got[t][2][b] - o2).norm() / o2.norm()
-            # value map: the 1e-3 parity bar.  obstacle map (a sigmoid probability, thresholded at 0.13 by the planner):
-            # absolute error; the tensor-core fp32 accumulator keeps ~17 bits, which the deeper decoder 2 amplifies more
-            assert e1 <= 1e-3 and e2 <= 1e-2 and l2 <= 1e-3, (float(e1), float(e2), float(l2))
+            # value map: max error relative to the map's maximum; obstacle map (a sigmoid probability in [0, 1], thresholded at
+            # 0.13 by the planner): absolute error and l2-relative error -- all at the 1e-3 parity bar
+            print(f"S={S} scene {b} step {t}: value map {float(e1):.2e}, obstacle map abs {float(e2):.2e} l2-rel {float(l2):.2e}")
+            assert e1 <= 1e-3 and e2 <= 1e-3 and l2 <= 1e-3, (float(e1), float(e2), float(l2))
             assert torch.equal(got[t][3][b], got[t][1][b].amax(dim=0))
-        assert grids[-1][:4].sum() > 1000 and grids[-1][4].sum() >= 9
+        assert grids[-1][:4].sum() > 1000 and grids[-1][4].sum() >= (9 if n_steps >= 3 else 1)
 
 
 def test_rollout_subsampled_statistics():
