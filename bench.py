@@ -15,9 +15,17 @@ The timed rollout starts at pose `--prefill` (default 50 = mid-rollout, the mean
 value  : inputs (meshes, trajectory cameras) resident in HBM, CUDA-event timed, max over ranks
 e2e    : same steps driven from HOST buffers: per step the camera poses are interpolated on the host, (R,T) copied
          from pinned memory, and the value maps / obstacle maps are read back to the host inside the timed region
-roofline: the dominant kernel (conv_gemm_f16, tcgen05) timed live with CUDA events around every launch
+roofline: the dominant kernel (conv_gemm_f16, tcgen05) timed live with CUDA events around every launch, over a second pass
+         of the same K steps with the network launched kernel by kernel (the `value` pass replays a captured CUDA graph of
+         the network, and events inside a captured graph cannot be timed)
 cpu_baseline: the oracle (CPU restatement of the reference path; the reference's own files cannot run here, see
-         DESIGN.md) timed on this box's host cores on a bounded sample: whole steps of ONE scene at the same state
+         DESIGN.md) timed on this box's host cores on a bounded sample: whole steps of ONE scene from the SAME state the
+         GPU arm is timed from (pose `prefill`)
+extra blocks (reported baselines / secondary configs, each outside the two timed regions above):
+  latency_b1     : NBP.forward at batch 1 (BASELINE configs[0]: the reference calls the net with one scene), 128^2 and 256^2
+  cudnn_baseline : the same network under torch + cuDNN on this GPU (fp32 with TF32 off, and TF32 on), "the kernel to beat"
+  train          : BASELINE configs[2] shape -- NBP fwd + loss + bwd + AdamW on 256^2 tiles, 64 tiles per GPU per optimizer
+                   step, NCCL all-reduce of the flat gradient across the N ranks
 """
 from __future__ import annotations
 
@@ -196,7 +204,7 @@ def run_ours(args):
     from nextbestpath_b200 import _lib, ops
     from nextbestpath_b200.networks import NBP
     from nextbestpath_b200.rollout import RolloutEngine, shard_scenes
-    from oracle import nbp_torch as NT            # only: golden weights + the cpu_baseline leg
+    from nextbestpath_b200 import synthetic as syn
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -214,10 +222,9 @@ def run_ours(args):
     B_total = args.scenes
     per = [shard_scenes(B_total, world, r)[1] for r in range(world)]
     first, B = shard_scenes(B_total, world, rank)
-    n_total = args.prefill + 2 * (args.warmup + args.steps) + 3
+    n_total = args.prefill + 2 * (args.warmup + args.steps) + (args.steps + 1) + 4
     scenes, poses, az = make_workload(B, args.level, n_total + 8, rank0_scene_index=first)
-    sd = NT.golden_state_dict(seed=9)
-    net = NBP(); net.load_state_dict(sd); net.to(dev).eval()
+    net = syn.calibrated_nbp(dev, seed=9)          # seeded weights, BatchNorm statistics calibrated on the CUDA train path
     net.precision = args.precision
     net.max_chunk = args.chunk
     eng = RolloutEngine(scenes, net, dev, S=S, max_steps=n_total + 1, seed=9)
@@ -227,7 +234,20 @@ def run_ours(args):
         eng.step(eng.upload_move(poses[:, t], poses[:, t + 1], az[:, t], az[:, t + 1]), run_network=False)
         t += 1
     torch.cuda.synchronize()
-    cloud_pts = eng.cloud_len.float().mean().item()
+
+    def all_mean(local_sum, local_n):
+        v = torch.tensor([float(local_sum), float(local_n)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(v)
+        return float(v[0] / v[1])
+
+    cloud_pts = all_mean(eng.cloud_len.double().sum().item(), B)                      # over ALL ranks' scenes
+    mean_faces = all_mean(sum(s.n_faces for s in scenes), B)
+    # state of scene 0 at pose `prefill`: what the cpu_baseline leg starts from (the same state the GPU arm is timed from)
+    cpu_state = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n0 = int(eng.cloud_len[0].item())
+        cpu_state = (eng.cloud[0, :n0].cpu().numpy(), list(eng.traj[0, : eng.traj_len_host].cpu().numpy()), t)
 
     def barrier():
         if world > 1:
@@ -248,7 +268,6 @@ def run_ours(args):
         sampler.start()
     barrier()
     launches0 = ops.launch_count()
-    _lib.check(L.nbp_conv_profile_begin(60000), "nbp_conv_profile_begin")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.warmup, n_run):
@@ -257,8 +276,6 @@ def run_ours(args):
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = ops.launch_count() - launches0
-    cms, cfl, cn, cdrop = ctypes.c_double(), ctypes.c_double(), ctypes.c_uint64(), ctypes.c_uint64()
-    _lib.check(L.nbp_conv_profile_end(ctypes.byref(cms), ctypes.byref(cfl), ctypes.byref(cn), ctypes.byref(cdrop)), "nbp_conv_profile_end")
     clocks = sampler.stop() if rank == 0 else None
     t += n_run
     ms_per_step = ms_total / args.steps
@@ -300,6 +317,24 @@ def run_ours(args):
     h2d = sum(x.numel() * x.element_size() for x in mv)
     d2h = sum(x.numel() * x.element_size() for x in (h_val, h_map8, h_obs))
 
+    t += n_run
+    # ================= roofline pass: the same K steps, network launched kernel by kernel, CUDA events around every conv launch
+    net.use_cuda_graph = False
+    moves = [eng.upload_move(poses[:, t + i], poses[:, t + i + 1], az[:, t + i], az[:, t + i + 1]) for i in range(args.steps + 1)]
+    eng.step(moves[0])
+    barrier()
+    _lib.check(L.nbp_conv_profile_begin(60000), "nbp_conv_profile_begin")
+    e0.record()
+    for i in range(1, args.steps + 1):
+        eng.step(moves[i])
+    e1.record()
+    barrier()
+    prof_ms_total = e0.elapsed_time(e1)
+    cms, cfl, cn, cdrop = ctypes.c_double(), ctypes.c_double(), ctypes.c_uint64(), ctypes.c_uint64()
+    _lib.check(L.nbp_conv_profile_end(ctypes.byref(cms), ctypes.byref(cfl), ctypes.byref(cn), ctypes.byref(cdrop)), "nbp_conv_profile_end")
+    net.use_cuda_graph = True
+    t += args.steps + 1
+
     # ================= roofline of the dominant kernel
     peaks = load_peaks()
     traffic = None
@@ -313,7 +348,10 @@ def run_ours(args):
                 "traffic": traffic, "traffic_source": "profiles/conv_traffic.json: mean dram read+write bytes of the launches in the committed ncu --set full capture",
                 "algorithmic_flops_per_launch_mean": conv_flops / max(int(cn.value), 1), "peak_source": peaks["which"],
                 "launches_timed": int(cn.value), "launches_dropped": int(cdrop.value), "kernel_ms_per_step": conv_ms / args.steps,
-                "share_of_step": conv_ms / ms_total if ms_total > 0 else None,
+                "share_of_step": conv_ms / prof_ms_total if prof_ms_total > 0 else None,
+                "timed_in": f"a second pass of the same {args.steps} steps with per-launch CUDA events and the network launched kernel by "
+                            f"kernel ({prof_ms_total / args.steps:.2f} ms/step there; the value pass replays the network as a CUDA graph)",
+                "step_ms_in_profiled_pass": prof_ms_total / args.steps,
                 "flops_counted": "algorithmic 2*M*N*K of the reference's convolutions (182.4 GFLOP per scene-step at 256x256; the fused "
                                  "upsample+conv layers are counted as the 3x3 conv on the upsampled image they replace); "
                                  + ("precision fp16x2 executes 3 tensor-core passes per executed flop, and the fused up-sampling "
@@ -321,44 +359,188 @@ def run_ours(args):
                                     if args.precision == "fp16x2" else "precision fp16: 1 pass"),
                 "mma_passes": 3 if args.precision == "fp16x2" else 1}
 
+    # ================= extra blocks (secondary configs and reported baselines; all outside the timed regions above)
+    del eng, moves
+    torch.cuda.empty_cache()
+    latency = None if args.no_extras else latency_b1(net, dev)
+    train = None if args.no_extras else train_block(args, dev, world, rank, max_over_ranks, barrier)
+    cudnn = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        cudnn = cudnn_baseline(net, dev, B_total, S, args.chunk, value)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ================= cpu_baseline (rank 0, N=1 only): bounded sample on the host cores
+    # ================= cpu_baseline (rank 0, N=1 only): bounded sample on the host cores, from the state the GPU arm was timed from
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if cpu_state is not None:
+        from oracle import nbp_torch as NT                          # the checker doubles as the CPU baseline (kind: "port")
         threads = os.cpu_count() or 1
-        n0 = int(eng.cloud_len[0].item())
-        cloud0 = eng.cloud[0, :n0].cpu().numpy()
-        traj0 = list(eng.traj[0, : eng.traj_len_host].cpu().numpy())
-        tcur = t + n_run                                             # engine state = pose tcur
-        times = cpu_steps(scenes[0], poses[0], az[0], cloud0, traj0, min(tcur, poses.shape[1] - 5), 1 + args.cpu_steps, S, sd, threads)
+        cloud0, traj0, t_state = cpu_state
+        times = cpu_steps(scenes[0], poses[0], az[0], cloud0, traj0, t_state, 1 + args.cpu_steps, S, NT.golden_state_dict(seed=9), threads)
         v = 1.0 / float(np.mean(times[1:]))
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_steps} whole scene-steps of scene 0 at its current state ({n0} cloud points) after 1 warm-up; "
-                         f"oracle port of the reference CPU path (naive rasteriser in C over {threads} threads, numpy histogram, torch fp32 NBP)"}
+               "sample": f"{args.cpu_steps} whole scene-steps of scene 0 from pose {t_state} ({len(cloud0)} cloud points: the state the GPU arm's "
+                         f"timed region starts from) after 1 warm-up; oracle port of the reference CPU path (naive rasteriser in C over "
+                         f"{threads} threads, numpy histogram, torch fp32 NBP)"}
 
+    full_cfg1 = (B_total == 256 and args.level == "simple" and S == 256)
+    full_cfg3 = (B_total == 128 and args.level == "insane" and S == 512 and world == 4)
+    label = "BASELINE configs[1]" if full_cfg1 else "BASELINE configs[3]" if full_cfg3 else \
+        f"a reduced / non-BASELINE configuration ({B_total} scenes, {args.level}, {S}x{S}, {world} GPU)"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f16x2 (split-fp16 operands, fp32 accumulate; fp32-grade results)" if args.precision == "fp16x2" else "f16 (fp32 accumulate)",
             "data": "synthetic",
-            "config": {"workload": f"{B_total} parallel AiMDoom-{args.level}-shaped scenes, {S}x{S} grid, inference rollout "
-                                   f"(BASELINE configs[{3 if (args.level == 'insane' and S == 512) else 1}])",
+            "config": {"workload": f"{B_total} parallel AiMDoom-{args.level}-shaped scenes, {S}x{S} grid, inference rollout ({label})",
                        "scenes_total": B_total, "scenes_per_gpu": per, "image": "256x456", "mesh_level": args.level,
-                       "mean_faces_per_scene": float(np.mean([s.n_faces for s in scenes])), "prefill_pose": args.prefill,
+                       "mean_faces_per_scene": mean_faces, "prefill_pose": args.prefill,
                        "mean_cloud_points_per_scene_at_start": cloud_pts, "nbp_chunk": args.chunk, "precision": args.precision,
+                       "network_launch": "CUDA graph replay (captured once per shape)",
                        "l2": "inputs larger than L2 (per-step working set > 5 GB: clouds, frames, activations)",
                        "parallelism": f"scenes sharded over {world} rank(s), no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "stage_ms": stage_ms,
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "latency_b1": latency, "cudnn_baseline": cudnn, "train": train}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ extra blocks
+def _time_ms(fn, n, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def latency_b1(net, dev):
+    """BASELINE configs[0]: the reference drivers call the network with ONE scene (nbp_planning.py:166,395).  Device time per
+    NBP.forward call at batch 1 through the drop-in module (graph replay + the copy of the input into the graph's buffer +
+    the clones the drop-in API returns), and the host wall time of the blocking call."""
+    from nextbestpath_b200 import synthetic as syn
+    out = {}
+    static = net.static_outputs
+    net.static_outputs = False
+    for S in (128, 256):
+        x = syn.count_like_input(1, S, seed=5).to(dev)
+        with torch.no_grad():
+            dev_ms = _time_ms(lambda: net(x), 30, warm=3)
+            torch.cuda.synchronize()
+            tic = time.perf_counter()
+            for _ in range(30):
+                o1, _ = net(x)
+                o1[0, 0, 0, 0].item()
+            wall_ms = (time.perf_counter() - tic) / 30 * 1e3
+        out[f"S{S}"] = {"device_ms": dev_ms, "blocking_call_ms": wall_ms, "gflop": FLOP_PER_SCENE_STEP[S] / 1e9}
+    net.static_outputs = static
+    out["note"] = "B = 1: one 128-pixel tile row per SM at the deep levels; latency is set by ~60 dependent kernels, not by tensor throughput"
+    return out
+
+
+def cudnn_baseline(net, dev, B_total, S, chunk, our_value):
+    """torch + cuDNN on the same GPU: the reference's nbp_model.py architecture (functional restatement, same weights) in eval
+    mode under no_grad, in chunks of `chunk` scenes -- fp32 with TF32 disabled (the arithmetic the parity bar is stated in) and
+    with TF32 enabled (cuDNN's tensor-core path; its value-map error against the fp32 run is reported).  Network only."""
+    from nextbestpath_b200 import synthetic as syn
+    from oracle import nbp_torch as NT                               # the functional torch restatement of nbp_model.py (a baseline, not the product)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    x = syn.count_like_input(chunk, S, seed=6).to(dev)
+    n_chunks = (B_total + chunk - 1) // chunk
+    res = {}
+    outs = {}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        torch.backends.cudnn.benchmark = True
+        for name, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            with torch.no_grad():
+                ms = _time_ms(lambda: NT.forward(sd, x), 3, warm=2)
+                outs[name] = NT.forward(sd, x)[0]
+            res[name] = {"ms_per_chunk": ms, "network_only_scene_steps_per_s": chunk / (ms / 1e3),
+                         "ms_per_256_scene_forward": ms * n_chunks,
+                         "algorithmic_tflops": chunk * FLOP_PER_SCENE_STEP[S] / (ms * 1e-3) / 1e12}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    with torch.no_grad():
+        net_static = net.static_outputs
+        net.static_outputs = False
+        ours = net(x)[0]
+        ours_ms = _time_ms(lambda: net(x), 5, warm=2)
+        net.static_outputs = net_static
+    ref = outs["fp32"]
+    rel = lambda a: float((a - ref).abs().max() / ref.abs().max())
+    res["tf32"]["value_map_max_rel_err_vs_cudnn_fp32"] = rel(outs["tf32"])
+    res["ours"] = {"ms_per_chunk": ours_ms, "network_only_scene_steps_per_s": chunk / (ours_ms / 1e3),
+                   "algorithmic_tflops": chunk * FLOP_PER_SCENE_STEP[S] / (ours_ms * 1e-3) / 1e12,
+                   "value_map_max_rel_err_vs_cudnn_fp32": rel(ours)}
+    res["speedup_vs_cudnn_fp32"] = res["fp32"]["ms_per_chunk"] / ours_ms
+    res["speedup_vs_cudnn_tf32"] = res["tf32"]["ms_per_chunk"] / ours_ms
+    res["note"] = (f"eval forward of {chunk} scenes at {S}x{S}, torch {torch.__version__} / cuDNN {torch.backends.cudnn.version()}, "
+                   "cudnn.benchmark on, same weights and input; the parity bar (1e-3) is met by ours and by cuDNN fp32 only")
+    return res
+
+
+def train_block(args, dev, world, rank, max_over_ranks, barrier):
+    """BASELINE configs[2] shape: train_nbp.py's optimizer step (nbp_utils.py:340-391) on 256x256 map tiles, 64 tiles per GPU
+    per optimizer step in micro-batches of 32 (gradients accumulated), ONE NCCL all-reduce of the flat 199.9 MB gradient per
+    step, AdamW.  tiles/s over all ranks; algorithmic FLOPs = 3 x forward."""
+    from nextbestpath_b200 import ops
+    from nextbestpath_b200 import synthetic as syn
+    from nextbestpath_b200.networks import NBP
+    from nextbestpath_b200.train import FlatGradAllReduce, train_step
+    S, K, tiles, micro = 256, 64, args.train_tiles, args.train_micro
+    net = NBP()
+    net.load_state_dict(syn.seeded_nbp_state_dict(net, 9))
+    net.to(dev)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)       # nbp_utils.py:228
+    red = FlatGradAllReduce(net.parameters())
+    g = torch.Generator().manual_seed(rank)
+    mbs = []
+    for i in range(0, tiles, micro):
+        b = min(micro, tiles - i)
+        x = syn.count_like_input(b, S, seed=100 * rank + i).to(dev)
+        tp = torch.stack((torch.randint(0, 8, (b, K), generator=g), torch.randint(0, S // 4, (b, K), generator=g),
+                          torch.randint(0, S // 4, (b, K), generator=g)), -1).to(dev)
+        mbs.append((x, tp, (torch.rand(b, K, generator=g) * 10).to(dev), (torch.rand(b, 1, S, S, generator=g) < 0.2).float().to(dev)))
+    loss = train_step(net, opt, mbs, red)
+    barrier()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n_steps = 2
+    ar_ms = 0.0
+    for _ in range(n_steps):
+        loss = train_step(net, opt, mbs, red)
+        ar_ms += red.last_ms()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / n_steps)
+    tiles_s = world * tiles / (ms / 1e3)
+    out = {"metric": "nbp_train_tiles_per_sec", "value": tiles_s, "unit": "tiles/s", "n_gpus": world, "ms_per_optimizer_step": ms,
+           "tiles_per_gpu_per_step": tiles, "global_tiles_per_step": world * tiles, "micro_batch": micro, "grid": S, "loss": float(loss),
+           "algorithmic_tflops": tiles_s * 3 * FLOP_PER_SCENE_STEP[S] / 1e12,
+           "frac_of_bf16_peak_per_gpu": tiles_s / world * 3 * FLOP_PER_SCENE_STEP[S] / 1e12 / load_peaks()["bf16"],
+           "grad_allreduce_bytes": red.flat.numel() * 4 if world > 1 else 0, "grad_allreduce_ms": ar_ms / n_steps if world > 1 else 0.0,
+           "gpu_launches_per_step": int((ops.launch_count() - l0) // n_steps), "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+           "workload": f"BASELINE configs[2] shape ({'the full 512-tile, 8-GPU configuration' if world == 8 and tiles == 64 else f'{world * tiles} tiles per step on {world} GPU'}): "
+                       "fp16x2 tcgen05 forward / dgrad / wgrad, train-mode BatchNorm, AdamW, synthetic count tiles"}
+    del net, opt, red, mbs
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -375,6 +557,9 @@ def main():
     ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "fp16"])
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the latency_b1 / cudnn_baseline / train blocks")
+    ap.add_argument("--train-tiles", type=int, default=64, help="tiles per GPU per optimizer step of the train block")
+    ap.add_argument("--train-micro", type=int, default=32)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -38,6 +38,9 @@ int nbp_version(void);
 const char* nbp_last_error(void);
 /* number of kernel launches this library has enqueued from the calling process (bench gpu_launches) */
 uint64_t nbp_launch_count(void);
+/* add n to that count: the host side replays captured CUDA graphs of this library's kernels (NBP.forward eval) and accounts
+ * for the kernels of each replay here */
+void nbp_count_launches(uint64_t n);
 
 /* ------------------------------------------------------------------------------------------ a2
  * Batched depth rasterisation.  Replaces Camera.capture_image's
@@ -154,6 +157,10 @@ typedef struct nbp_conv_desc {
                                               fp32 accumulator before the partial sum is folded into fp32 round-to-nearest registers;
                                               0 = default (8).  Smaller = more accurate, slower (measured: 8 -> 3.6e-5 network error,
                                               2 -> floor of the 22-bit operands, -10 % throughput) */
+    void* pool_dst; int pool_ld; int pool_lo_off; /* optional (NULL = off): ALSO write nn.MaxPool2d(2,2) of the output (nbp_model.py:68,113-121)
+                                              as an NHWC fp16 tensor [n][h/2][w/2][pool_ld] (lo plane pool_lo_off elements after the hi
+                                              channels), fused into the epilogue: the encoder needs both the skip tensor and its pooled
+                                              copy.  h, w even; not with up2x / out_f32 */
 } nbp_conv_desc;
 
 /* tcgen05/TMEM/TMA implicit-GEMM convolution: conv_block / up_conv / Attention_block W_g,W_x (nbp_model.py:8-62) */
@@ -180,9 +187,10 @@ int nbp_att_gate(const void* a, int f_int, int ld_a, int lo_a, const void* x, in
                  const float* w_psi, float psi_scale, float psi_shift,
                  void* dst, int dst_ld, int dst_c_off, int dst_lo, int64_t npix, void* stream);
 /* Final1 (256->8) and Final2 (64->1, sigmoid) (nbp_model.py:89,106-108): NHWC fp16 in, NCHW fp32 out [n,c_out,hw];
- * weight fp32 [c_out][c_in], c_out in {1, 8} */
+ * weight fp32 [c_out][c_in], c_out in {1, 8}.  dst_max (optional, NULL = off): [n,hw] fp32 = max over the c_out channels, the
+ * heading read-out `torch.max(predicted_value_map, dim=1)` of next_best_path/testers/nbp_planning.py:193 fused into the head */
 int nbp_conv1x1_head(const void* src, int c_in, int ld_src, int lo_src, const float* weight, const float* bias, int c_out,
-                     int sigmoid, float* dst, int n, int64_t hw, void* stream);
+                     int sigmoid, float* dst, float* dst_max, int n, int64_t hw, void* stream);
 
 /* ------------------------------------------------------------------------------------------ a11 (train mode), a13
  * Train-mode BatchNorm2d (batch statistics, running-stat update: momentum 0.1, unbiased running variance, eps 1e-5 --

@@ -22,6 +22,7 @@ SIGNATURES = {
     "nbp_version": (_i, []),
     "nbp_last_error": (C.c_char_p, []),
     "nbp_launch_count": (C.c_uint64, []),
+    "nbp_count_launches": (None, [C.c_uint64]),
     "nbp_raster_workspace_bytes": (_z, [_i, _l]),
     "nbp_raster_depth_batched": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _i, _l, _i, _i, _i, _f, _f, _p, _p, _p, _z, _p]),
     "nbp_backproject_workspace_bytes": (_z, [_i]),
@@ -40,7 +41,7 @@ class ConvDesc(C.Structure):
                 ("src1", _p), ("c1", _i), ("ld1", _i), ("lo1", _i),
                 ("n", _i), ("h", _i), ("w", _i), ("taps", _i), ("up2x", _i), ("weight", _p), ("c_out", _i),
                 ("scale", _p), ("shift", _p), ("relu", _i), ("dst", _p), ("dst_ld", _i), ("dst_c_off", _i),
-                ("dst_lo_off", _i), ("out_f32", _i), ("k_chunk", _i)]
+                ("dst_lo_off", _i), ("out_f32", _i), ("k_chunk", _i), ("pool_dst", _p), ("pool_ld", _i), ("pool_lo_off", _i)]
 
 
 SIGNATURES.update({
@@ -51,7 +52,7 @@ SIGNATURES.update({
     "nbp_maxpool2x2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     "nbp_upsample2x": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     "nbp_att_gate": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p, _f, _f, _p, _i, _i, _i, _l, _p]),
-    "nbp_conv1x1_head": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _i, _l, _p]),
+    "nbp_conv1x1_head": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _l, _p]),
 })
 
 _d = C.c_double

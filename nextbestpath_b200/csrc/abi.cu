@@ -38,3 +38,4 @@ void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxe
 extern "C" int nbp_version(void) { return NBP_ABI_VERSION; }
 extern "C" const char* nbp_last_error(void) { return nbp::g_err; }
 extern "C" uint64_t nbp_launch_count(void) { return nbp::g_launches.load(std::memory_order_relaxed); }
+extern "C" void nbp_count_launches(uint64_t n) { nbp::count_launch(n); }

@@ -68,6 +68,7 @@ struct ConvKParams {
     const float* scale; const float* shift;
     int relu;
     __half* dst; int dst_ld, dst_c_off, dst_lo_off;
+    __half* pool; int pool_ld, pool_lo_off;   // optional second output: the 2x2 max-pooled activation [n][h/2][w/2] (fused nn.MaxPool2d)
 };
 
 template <int BLOCK_N, bool PRECISE, int HALO>     // HALO = 0: plain stages; 2 | 3: halo stages carrying that many taps
@@ -280,31 +281,48 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                     }
                     return;
                 }
-                uint32_t packed[16], packed_lo[16];
+                float a[32];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int col = c * 32 + 2 * j;
-                    float a0 = fmaf(v[2 * j], sa[col], sa[BLOCK_N + col]);
-                    float a1 = fmaf(v[2 * j + 1], sa[col + 1], sa[BLOCK_N + col + 1]);
-                    if (p.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); }
-                    a0 = fminf(fmaxf(a0, -65504.0f), 65504.0f);
-                    a1 = fminf(fmaxf(a1, -65504.0f), 65504.0f);
-                    const __half2 h = __floats2half2_rn(a0, a1);
-                    packed[j] = *reinterpret_cast<const uint32_t*>(&h);
-                    if (PRECISE) {
-                        const float2 hf = __half22float2(h);
-                        const __half2 l = __floats2half2_rn((a0 - hf.x) * 2048.0f, (a1 - hf.y) * 2048.0f);
-                        packed_lo[j] = *reinterpret_cast<const uint32_t*>(&l);
-                    }
+                for (int j = 0; j < 32; ++j) {
+                    const int col = c * 32 + j;
+                    float t = fmaf(v[j], sa[col], sa[BLOCK_N + col]);
+                    if (p.relu) t = fmaxf(t, 0.0f);
+                    a[j] = fminf(fmaxf(t, -65504.0f), 65504.0f);
                 }
-                if (valid) {
-                    uint4* o = reinterpret_cast<uint4*>(orow + c * 32);
+                // fp32 -> fp16 planes (hi [, (x - hi) * 2048]) -> 16-byte stores
+                auto split_store = [&](__half* row, int lo_off, const float* x) {
+                    uint32_t packed[16], packed_lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const __half2 h = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+                        packed[j] = *reinterpret_cast<const uint32_t*>(&h);
+                        if (PRECISE) {
+                            const float2 hf = __half22float2(h);
+                            const __half2 l = __floats2half2_rn((x[2 * j] - hf.x) * 2048.0f, (x[2 * j + 1] - hf.y) * 2048.0f);
+                            packed_lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+                        }
+                    }
+                    uint4* o = reinterpret_cast<uint4*>(row);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) o[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
                     if (PRECISE) {
-                        uint4* ol = reinterpret_cast<uint4*>(orow + p.dst_lo_off + c * 32);
+                        uint4* ol = reinterpret_cast<uint4*>(row + lo_off);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) ol[j] = make_uint4(packed_lo[4 * j], packed_lo[4 * j + 1], packed_lo[4 * j + 2], packed_lo[4 * j + 3]);
+                    }
+                };
+                if (valid) split_store(orow + c * 32, p.dst_lo_off, a);
+                if (p.pool) {
+                    // fused nn.MaxPool2d(2,2): the 2x2 window of a pixel lives in lanes {l, l^1, l^tw, l^(tw+1)} of this warp (tile rows
+                    // are tw <= 16 pixels wide and a warp holds 32 consecutive tile pixels); max commutes with the monotonic hi/lo split
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float t = fmaxf(a[j], __shfl_xor_sync(0xffffffffu, a[j], 1));
+                        a[j] = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, p.tw));
+                    }
+                    if (valid && !((wi | hi) & 1)) {
+                        const size_t ppix = ((size_t)nn * (p.h >> 1) + (y >> 1)) * (size_t)(p.w >> 1) + (x >> 1);
+                        split_store(p.pool + ppix * p.pool_ld + n_tile * BLOCK_N + c * 32, p.pool_lo_off, a);
                     }
                 }
             };
@@ -524,6 +542,15 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     kp.b_rows_per_parity = (precise ? 2 : 1) * d->c_out;
     kp.scale = d->scale; kp.shift = d->shift; kp.relu = d->relu;
     kp.dst = (__half*)d->dst; kp.dst_ld = d->dst_ld; kp.dst_c_off = d->dst_c_off; kp.dst_lo_off = d->dst_lo_off;
+    kp.pool = (__half*)d->pool_dst; kp.pool_ld = d->pool_ld; kp.pool_lo_off = d->pool_lo_off;
+    if (d->pool_dst) {
+        if (d->up2x || d->out_f32) return invalid("nbp_conv_fwd: pool_dst cannot be combined with up2x / out_f32");
+        if ((d->h | d->w) & 1) return invalid("nbp_conv_fwd: pool_dst needs even h and w (got %d x %d)", d->h, d->w);
+        if (kp.tw < 2 || kp.tw > 16 || kp.th < 2) return invalid("nbp_conv_fwd: pool_dst needs a tile of >= 2 rows of 2..16 pixels (w=%d h=%d)", d->w, d->h);
+        if (d->pool_ld % 8 || d->pool_lo_off % 8 || (precise ? d->pool_lo_off : 0) + d->c_out > d->pool_ld || (precise && d->pool_lo_off < d->c_out) ||
+            ((uintptr_t)d->pool_dst & 15))
+            return invalid("nbp_conv_fwd: bad pooled destination layout ld=%d lo_off=%d c_out=%d", d->pool_ld, d->pool_lo_off, d->c_out);
+    }
     if (kp.tn > 256 || kp.th > 256) return invalid("nbp_conv_fwd: image too small for a 128-pixel tile (w=%d h=%d)", d->w, d->h);
 
     CUtensorMap a0, a1, b;

@@ -188,7 +188,7 @@ template <int COUT>
 __global__ void __launch_bounds__(256) conv1x1_head_kernel(const __half* __restrict__ src, int c_in, int ld_src, int lo_src,
                                                            const float* __restrict__ wt,     // [COUT][c_in]
                                                            const float* __restrict__ bias, int sigmoid,
-                                                           float* __restrict__ dst, int n, size_t hw) {
+                                                           float* __restrict__ dst, float* __restrict__ dst_max, int n, size_t hw) {
     extern __shared__ float s_w[];
     for (int i = threadIdx.x; i < COUT * c_in; i += blockDim.x) s_w[i] = wt[i];
     __syncthreads();
@@ -209,12 +209,15 @@ __global__ void __launch_bounds__(256) conv1x1_head_kernel(const __half* __restr
             }
         }
         const size_t img = pix / hw, rem = pix - img * hw;
+        float vmax = -INFINITY;
 #pragma unroll
         for (int c = 0; c < COUT; ++c) {
             float v = acc[c];
             if (sigmoid) v = 1.0f / (1.0f + expf(-v));
             dst[(img * COUT + c) * hw + rem] = v;
+            vmax = fmaxf(vmax, v);
         }
+        if (dst_max) dst_max[pix] = vmax;                  // torch.max(predicted_value_map, dim=1) (nbp_planning.py:193)
     }
 }
 
@@ -303,7 +306,7 @@ extern "C" int nbp_att_gate(const void* a, int f_int, int ld_a, int lo_a, const 
 }
 
 extern "C" int nbp_conv1x1_head(const void* src, int c_in, int ld_src, int lo_src, const float* weight, const float* bias, int c_out,
-                                int sigmoid, float* dst, int n, int64_t hw, void* stream) {
+                                int sigmoid, float* dst, float* dst_max, int n, int64_t hw, void* stream) {
     if (!src || !weight || !bias || !dst) return invalid("nbp_conv1x1_head: null pointer argument");
     if (c_in <= 0 || c_in % 8 || n <= 0 || hw <= 0) return invalid("nbp_conv1x1_head: bad sizes");
     int rc = check_plane("nbp_conv1x1_head", c_in, ld_src, lo_src);
@@ -312,8 +315,8 @@ extern "C" int nbp_conv1x1_head(const void* src, int c_in, int ld_src, int lo_sr
     const size_t smem = sizeof(float) * (size_t)c_out * c_in;
     const int g = grid_for((size_t)n * hw, 256);
     cudaStream_t st = (cudaStream_t)stream;
-    if (c_out == 8) conv1x1_head_kernel<8><<<g, 256, smem, st>>>((const __half*)src, c_in, ld_src, lo_src, weight, bias, sigmoid, dst, n, (size_t)hw);
-    else if (c_out == 1) conv1x1_head_kernel<1><<<g, 256, smem, st>>>((const __half*)src, c_in, ld_src, lo_src, weight, bias, sigmoid, dst, n, (size_t)hw);
+    if (c_out == 8) conv1x1_head_kernel<8><<<g, 256, smem, st>>>((const __half*)src, c_in, ld_src, lo_src, weight, bias, sigmoid, dst, dst_max, n, (size_t)hw);
+    else if (c_out == 1) conv1x1_head_kernel<1><<<g, 256, smem, st>>>((const __half*)src, c_in, ld_src, lo_src, weight, bias, sigmoid, dst, dst_max, n, (size_t)hw);
     else return invalid("nbp_conv1x1_head: c_out must be 1 or 8 (got %d)", c_out);
     count_launch();
     return check_cuda(cudaGetLastError(), "nbp_conv1x1_head launch");

@@ -71,6 +71,13 @@ class NBP(nn.Module):
         # "fp16x2": split-fp16 operands, fp32-grade results (7e-6 of the fp32 reference) -- the parity path.
         # "fp16"  : single fp16 plane, 3x fewer tensor-core passes, ~7e-3 of the fp32 reference.
         self.precision = "fp16x2"
+        # eval forward = replay of a captured CUDA graph (see _run_eval).  static_outputs: return the graph's own output buffers
+        # (overwritten by the next forward) instead of copies -- for callers that consume the maps before the next call.
+        self.bn_momentum = 0.1         # nn.BatchNorm2d default, as the reference instantiates it (nbp_model.py:12); train mode only
+        self.use_cuda_graph = True
+        self.static_outputs = False
+        self._graphs = {}
+        self.last_value_max = None
 
     # ------------------------------------------------------------------ reference API
     def forward(self, x):
@@ -90,14 +97,36 @@ class NBP(nn.Module):
                 if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
                     raise RuntimeError(f"parameter {n} must be a contiguous fp32 CUDA tensor")
             return NBPTrainFunction.apply(self, x, tuple(n for n, _ in named), *[p for _, p in named])
-        outs1, outs2 = [], []
         pk = self._pack(x.device)
+        out1, out2, vmax = self._run_eval(pk, x)
+        self.last_value_max = vmax                     # (B, S/4, S/4): max over the 8 headings (nbp_planning.py:193), fused
+        return out1, out2
+
+    def _run_eval(self, pk, x):
+        """Eval forward of the whole batch in chunks of ``max_chunk`` scenes.  With ``use_cuda_graph`` the chunk loop is
+        captured once per (weights, shape) into a CUDA graph reading a module-owned input buffer and replayed afterwards
+        (~40 kernels per chunk; tensor maps, launch parameters and the activation arena are frozen in the graph)."""
+        B, _, S, S2 = x.shape
+        dev = x.device
+        if not self.use_cuda_graph or torch.cuda.is_current_stream_capturing():
+            out1 = torch.empty((B, self.output_ch1, S // 4, S2 // 4), dtype=torch.float32, device=dev)
+            out2 = torch.empty((B, self.output_ch2, S, S2), dtype=torch.float32, device=dev)
+            vmax = torch.empty((B, S // 4, S2 // 4), dtype=torch.float32, device=dev)
+            self._eval_chunks(pk, x, out1, out2, vmax)
+            return out1, out2, vmax
+        key = (id(pk), B, S, S2, dev.index, self.max_chunk)
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= 4:                  # bound the memory held by graph pools (shapes seen long ago)
+                self._graphs.pop(next(iter(self._graphs)))
+            g = _EvalGraph(self, pk, x)
+            self._graphs[key] = g
+        return g.replay(x, clone=not self.static_outputs)
+
+    def _eval_chunks(self, pk, x, out1, out2, vmax):
         for b0 in range(0, x.shape[0], self.max_chunk):
-            o1, o2 = _forward_eval(pk, x[b0:b0 + self.max_chunk])
-            outs1.append(o1); outs2.append(o2)
-        if len(outs1) == 1:
-            return outs1[0], outs2[0]
-        return torch.cat(outs1), torch.cat(outs2)
+            b1 = min(x.shape[0], b0 + self.max_chunk)
+            _forward_eval(pk, x[b0:b1], out1[b0:b1], out2[b0:b1], vmax[b0:b1])
 
     def loss(self, pred1, target1, pred2, target2):
         """nbp_model.py:162-173: MSE/(2 s1^2) + log s1 + BCE/s2^2 + log s2 with s = exp(log_vars)."""
@@ -116,6 +145,7 @@ class NBP(nn.Module):
         sd = {k: v.detach().to(device=device, dtype=torch.float32) if v.is_floating_point() else v for k, v in self.state_dict().items()}
         pk = pack_state_dict(sd, precise=self.precision == "fp16x2")
         self._packed = (key, pk)
+        self._graphs.clear()                            # graphs bake in the packed-weight pointers
         return pk
 
 
@@ -222,17 +252,55 @@ class _Act:
         return _Act(self.t, c, self.ld, self.lo, self.h, self.w, self.off + off)
 
 
-def _conv(pk, layer, B, src0, taps, dst, relu=True, src1=None, up2x=False, k_chunk=0):
+def _conv(pk, layer, B, src0, taps, dst, relu=True, src1=None, up2x=False, k_chunk=0, pool=None):
     d = _lib.ConvDesc(1 if pk["precise"] else 0, src0.ptr, src0.c, src0.ld, src0.lo,
                       src1.ptr if src1 is not None else None, src1.c if src1 is not None else 0,
                       src1.ld if src1 is not None else 0, src1.lo if src1 is not None else 0,
                       B, src0.h, src0.w, taps, 1 if up2x else 0, layer["w"].data_ptr(), layer["c_out"],
                       layer["scale"].data_ptr(), layer["shift"].data_ptr(), 1 if relu else 0,
-                      dst.t.data_ptr(), dst.ld, dst.off, dst.lo, 0, k_chunk)
+                      dst.t.data_ptr(), dst.ld, dst.off, dst.lo, 0, k_chunk,
+                      pool.ptr if pool is not None else None, pool.ld if pool is not None else 0, pool.lo if pool is not None else 0)
     _lib.check(_lib.lib().nbp_conv_fwd(ctypes.byref(d), _stream()), "nbp_conv_fwd")
 
 
-def _forward_eval(pk, x):
+class _EvalGraph:
+    """One captured eval forward: static input / output buffers + the CUDA graph of every kernel of every chunk."""
+
+    def __init__(self, module, pk, x):
+        B, C, S, S2 = x.shape
+        dev = x.device
+        self.pk = pk                                    # keeps the packed weights (whose pointers the graph holds) alive
+        self.x = torch.empty_like(x)
+        self.out1 = torch.empty((B, module.output_ch1, S // 4, S2 // 4), dtype=torch.float32, device=dev)
+        self.out2 = torch.empty((B, module.output_ch2, S, S2), dtype=torch.float32, device=dev)
+        self.vmax = torch.empty((B, S // 4, S2 // 4), dtype=torch.float32, device=dev)
+        self.x.copy_(x)
+        L = _lib.lib()
+        # eager warm-up on a side stream (one-time kernel attribute set-up must not happen inside the capture)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            _forward_eval(pk, self.x[: min(B, module.max_chunk)], self.out1[: min(B, module.max_chunk)],
+                          self.out2[: min(B, module.max_chunk)], self.vmax[: min(B, module.max_chunk)])
+        torch.cuda.current_stream(dev).wait_stream(side)
+        n0 = L.nbp_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            module._eval_chunks(pk, self.x, self.out1, self.out2, self.vmax)
+        self.n_kernels = int(L.nbp_launch_count() - n0)
+
+    def replay(self, x, clone):
+        if x.data_ptr() != self.x.data_ptr():
+            self.x.copy_(x)
+        self.graph.replay()
+        _lib.lib().nbp_count_launches(self.n_kernels)
+        if clone:
+            return self.out1.clone(), self.out2.clone(), self.vmax.clone()
+        return self.out1, self.out2, self.vmax
+
+
+def _forward_eval(pk, x, out1, out2, vmax):
+    """One chunk: x (B,5,S,S) fp32 -> out1 (B,8,S/4,S/4), out2 (B,1,S,S), vmax (B,S/4,S/4), written in place."""
     L = _lib.lib()
     dev = x.device
     B, _, S, S2 = x.shape
@@ -243,13 +311,15 @@ def _forward_eval(pk, x):
         return _Act(torch.empty((B, h, w, planes * c), dtype=torch.float16, device=dev), c, planes * c,
                     c if planes == 2 else 0, h, w)
 
-    def double_conv(name, src):
+    def double_conv(name, src, pooled=False):
+        """conv_block (nbp_model.py:8-21); ``pooled``: the second conv also writes MaxPool2d(2,2) of its output (:113-121)."""
         c_out = pk[name + ".a"]["c_out"]
         t = new(src.h, src.w, c_out)
         _conv(pk, pk[name + ".a"], B, src, 9, t)
         y = new(src.h, src.w, c_out)
-        _conv(pk, pk[name + ".b"], B, t, 9, y)
-        return y
+        p = new(src.h // 2, src.w // 2, c_out) if pooled else None
+        _conv(pk, pk[name + ".b"], B, t, 9, y, pool=p)
+        return y, p
 
     # ---- encoder
     a = new(S, S2, 64)
@@ -257,15 +327,12 @@ def _forward_eval(pk, x):
     _lib.check(L.nbp_conv_first(x.data_ptr(), B, stem["c_in"], S, S2, stem["w"].data_ptr(), stem["scale"].data_ptr(),
                                 stem["shift"].data_ptr(), 64, 1, a.ptr, a.ld, a.lo, st), "nbp_conv_first")
     x1 = new(S, S2, 64)
-    _conv(pk, pk["Conv1.b"], B, a, 9, x1)
+    p = new(S // 2, S2 // 2, 64)
+    _conv(pk, pk["Conv1.b"], B, a, 9, x1, pool=p)
     del a
     skips = {1: x1}
-    cur = x1
     for lvl in range(2, 6):
-        p = new(cur.h // 2, cur.w // 2, cur.c)
-        _lib.check(L.nbp_maxpool2x2(cur.ptr, B, cur.h, cur.w, cur.c, cur.ld, cur.lo, p.ptr, p.ld, p.lo, st), "nbp_maxpool2x2")
-        cur = double_conv(f"Conv{lvl}", p)
-        skips[lvl] = cur
+        skips[lvl], p = double_conv(f"Conv{lvl}", p, pooled=lvl < 5)
 
     def decoder_stage(d, lvl, dec):
         """Up{lvl}_{dec} -> Att{lvl}_{dec} -> cat -> Up_conv{lvl}_{dec} (nbp_model.py:124-129)."""
@@ -283,21 +350,20 @@ def _forward_eval(pk, x):
                                   att["w_psi"].data_ptr(), att["psi_scale"], att["psi_shift"],
                                   gated.t.data_ptr(), gated.ld, gated.off, gated.lo, B * skip.h * skip.w, st), "nbp_att_gate")
         del arelu
-        return double_conv(f"Up_conv{t}", cat)
+        return double_conv(f"Up_conv{t}", cat)[0]
 
-    def head(name, d, sigmoid):
-        out = torch.empty((B, pk[name]["w"].shape[0], d.h, d.w), dtype=torch.float32, device=dev)
+    def head(name, d, sigmoid, out, out_max=None):
         _lib.check(L.nbp_conv1x1_head(d.ptr, d.c, d.ld, d.lo, pk[name]["w"].data_ptr(), pk[name]["b"].data_ptr(),
-                                      out.shape[1], 1 if sigmoid else 0, out.data_ptr(), B, d.h * d.w, st), "nbp_conv1x1_head")
-        return out
+                                      out.shape[1], 1 if sigmoid else 0, out.data_ptr(),
+                                      out_max.data_ptr() if out_max is not None else None, B, d.h * d.w, st), "nbp_conv1x1_head")
 
-    # ---- decoder 1 -> value map at S/4
+    assert out1.is_contiguous() and out2.is_contiguous() and vmax.is_contiguous()
+    # ---- decoder 1 -> value map at S/4 (+ its max over the 8 headings)
     d = decoder_stage(skips[5], 5, 1)
     d = decoder_stage(d, 4, 1)
-    out1 = head("Final1", d, False)
+    head("Final1", d, False, out1, vmax)
     # ---- decoder 2 -> obstacle map at S
     d = decoder_stage(skips[5], 5, 2)
     for lvl in (4, 3, 2):
         d = decoder_stage(d, lvl, 2)
-    out2 = head("Final2", d, True)
-    return out1, out2
+    head("Final2", d, True, out2)

@@ -34,8 +34,9 @@ def _st():
 class _Tape:
     """Everything one forward pass saves for its backward pass."""
 
-    def __init__(self, dev, B, cache=None):
+    def __init__(self, dev, B, cache=None, momentum=None):
         self.dev, self.B = dev, B
+        self.momentum = BN_MOMENTUM if momentum is None else float(momentum)
         self.cache = cache if cache is not None else {}     # packed GEMM weights, valid until the parameters change
         self.L = _lib.lib()
         self.ws = torch.zeros(2 * 2048 + 16, dtype=torch.float64, device=dev)        # fp64 reduction scratch
@@ -114,7 +115,7 @@ def _bn_stats(t, z, npix, bn):
     C = z.c
     stats = t.f32(4, C)
     _chk(t.L.nbp_bn_train_stats(z.ptr, z.ld, z.lo, npix, C, bn["weight"].data_ptr(), bn["bias"].data_ptr(),
-                                bn["running_mean"].data_ptr(), bn["running_var"].data_ptr(), BN_MOMENTUM, BN_EPS,
+                                bn["running_mean"].data_ptr(), bn["running_var"].data_ptr(), t.momentum, BN_EPS,
                                 stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
                                 t.ws.data_ptr(), _st()), "nbp_bn_train_stats")
     bn["num_batches_tracked"].add_(1)
@@ -207,13 +208,13 @@ def _cbr(t, sd, conv, bn, src, taps=9, dst=None, relu=True):
     return y, backward
 
 
-def forward_train(sd, x, cache=None, capture=False):
+def forward_train(sd, x, cache=None, capture=False, momentum=None):
     """sd: name -> CUDA fp32 tensor (parameters and BatchNorm buffers; buffers are updated in place).
     ``cache``: dict that outlives the call and holds the packed GEMM weights (the caller drops it when parameters change).
     Returns (out1, out2, tape)."""
     dev = x.device
     B, cin0, S, S2 = x.shape
-    t = _Tape(dev, B, cache)
+    t = _Tape(dev, B, cache, momentum)
     if capture:
         t.capture = {}
     L = t.L
@@ -290,7 +291,7 @@ def forward_train(sd, x, cache=None, capture=False):
         b_psi = sd[f"Att{tg}.psi.0.bias"]
         zpsi, stat4, psi = t.f32(npix), t.f32(4), t.f32(npix)
         _chk(L.nbp_psi_train(a.ptr, a.ld, a.lo, npix, f_int, w_psi.data_ptr(), b_psi.data_ptr(), bn1["weight"].data_ptr(), bn1["bias"].data_ptr(),
-                             bn1["running_mean"].data_ptr(), bn1["running_var"].data_ptr(), BN_MOMENTUM, BN_EPS, zpsi.data_ptr(), stat4.data_ptr(),
+                             bn1["running_mean"].data_ptr(), bn1["running_var"].data_ptr(), t.momentum, BN_EPS, zpsi.data_ptr(), stat4.data_ptr(),
                              t.ws.data_ptr(), st), "nbp_psi_train")
         bn1["num_batches_tracked"].add_(1)
         _chk(L.nbp_att_apply(zpsi.data_ptr(), stat4[2:3].data_ptr(), stat4[3:4].data_ptr(), skip.ptr, skip.ld, skip.lo, npix, f_l,
@@ -330,7 +331,7 @@ def forward_train(sd, x, cache=None, capture=False):
         w, b = sd[name + ".weight"], sd[name + ".bias"]
         w2 = w[:, :, 0, 0].contiguous()
         out = torch.empty((B, w.shape[0], d.h, d.w), dtype=torch.float32, device=dev)
-        _chk(L.nbp_conv1x1_head(d.ptr, d.c, d.ld, d.lo, w2.data_ptr(), b.data_ptr(), w.shape[0], 1 if sigmoid else 0, out.data_ptr(), B, d.h * d.w, st),
+        _chk(L.nbp_conv1x1_head(d.ptr, d.c, d.ld, d.lo, w2.data_ptr(), b.data_ptr(), w.shape[0], 1 if sigmoid else 0, out.data_ptr(), None, B, d.h * d.w, st),
              "nbp_conv1x1_head")
 
         def backward(dout):
@@ -430,7 +431,8 @@ class NBPTrainFunction(torch.autograd.Function):
         if cache is None or cache.get("key") != key:
             cache = {"key": key}
             module._train_pack = cache
-        out1, out2, tape = forward_train(sd, x.contiguous().float(), cache, capture=bool(getattr(module, "capture_decisions", False)))
+        out1, out2, tape = forward_train(sd, x.contiguous().float(), cache, capture=bool(getattr(module, "capture_decisions", False)),
+                                          momentum=getattr(module, "bn_momentum", None))
         if tape.capture is not None:
             module.last_decisions = decisions_from_capture(tape.capture)
             tape.capture = None

@@ -13,7 +13,8 @@ One step per scene = one ``pose_i`` iteration of ``compute_nbp_trajectory``
 The planner, collision checks, coverage metric and disk I/O of the reference are out of scope: the
 next key pose of every scene is an input of ``step``.  Frames never leave HBM (the reference writes
 each one to disk and reloads it, macarons_utils.py:2782,:992).  All state lives in preallocated device
-buffers; a step enqueues ~85 kernels and performs no host synchronisation.
+buffers; a step enqueues ~25 geometry kernels plus one CUDA-graph replay of the network (stage C) and performs no host
+synchronisation.
 """
 from __future__ import annotations
 
@@ -94,6 +95,9 @@ class RolloutEngine:
                  sensor_range=70.0, grid_range=(-40.0, 40.0), n_pieces=4, seed=9):
         self.dev = torch.device(device)
         self.nbp = nbp
+        # the engine consumes (or copies out) the maps of a step before it runs the next forward: let NBP.forward hand out the
+        # output buffers of its captured graph instead of clones.  StepOutput tensors are therefore valid until the next step().
+        nbp.static_outputs = True
         self.B, self.S, self.H, self.W = len(scenes), S, H, W
         self.gf, self.sensor_range, self.grid_range, self.n_pieces, self.seed = gathering_factor, sensor_range, grid_range, n_pieces, seed
         dev = self.dev
@@ -224,9 +228,11 @@ class RolloutEngine:
                              max_points=self.max_points_bound, out=self.grid)
             mark()
             # ---- C: network
+            if self._copy_done is not None:                      # the previous step's read-back still owns the output buffers
+                torch.cuda.current_stream(self.dev).wait_event(self._copy_done)
             with torch.no_grad():
                 out1, out2 = self.nbp(self.grid)
-            vmax = out1.amax(dim=1)
+            vmax = self.nbp.last_value_max                       # max over the 8 headings, fused into the Final1 kernel (row a14)
             mark()
             if host_out is not None:
                 if self._copy_stream is None:

@@ -159,3 +159,75 @@ def sample_surface(scene: Scene, n_points: int, seed: int) -> np.ndarray:
     u[flip], v[flip] = 1.0 - u[flip], 1.0 - v[flip]
     p = tri[f, 0] + u[:, None] * (tri[f, 1] - tri[f, 0]) + v[:, None] * (tri[f, 2] - tri[f, 0])
     return p.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ seeded network weights / inputs
+def count_like_input(B: int, S: int, seed: int = 8, density: float = 0.04, rate: float = 25.0, n_traj: int = 20):
+    """Synthetic model input shaped like nbp_planning.py:126-132: 4 sparse count images + a sparse 0/1 trajectory image
+    (integer-valued fp32, host tensor).  Same recipe (and, for a seed, the same values) as the oracle's generator."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = torch.zeros(B, 5, S, S)
+    occ = (torch.rand(B, 4, S, S, generator=g) < density).float()
+    x[:, :4] = occ * (1.0 + torch.poisson(torch.full((B, 4, S, S), rate), generator=g))
+    idx = torch.randint(0, S, (B, n_traj, 2), generator=g)
+    for b in range(B):
+        x[b, 4, idx[b, :, 0], idx[b, :, 1]] = 1.0
+    return x
+
+
+def seeded_nbp_state_dict(net, seed: int = 9):
+    """Deterministic, well-conditioned weights for an ``NBP`` module, independent of torch's initialisers: conv weights
+    U(-b, b) with b = sqrt(3 / fan_in), small biases, BatchNorm gamma in [0.8, 1.2], beta in [-0.1, 0.1], running_mean in
+    [-0.2, 0.2], running_var in [0.6, 1.4]; drawn in state_dict order from one generator (there are no checkpoints offline:
+    README.md:71-80 links them)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    u = lambda shape, lo, hi: torch.rand(tuple(shape), generator=g, dtype=torch.float32) * (hi - lo) + lo
+    sd = {}
+    for key, ref in net.state_dict().items():
+        if key == "log_vars":
+            sd[key] = torch.zeros_like(ref, device="cpu")
+        elif key.endswith("num_batches_tracked"):
+            sd[key] = torch.tensor(0, dtype=torch.long)
+        elif key.endswith("running_mean"):
+            sd[key] = u(ref.shape, -0.2, 0.2)
+        elif key.endswith("running_var"):
+            sd[key] = u(ref.shape, 0.6, 1.4)
+        elif ref.dim() == 4:
+            fan_in = ref.shape[1] * ref.shape[2] * ref.shape[3]
+            b = (3.0 / fan_in) ** 0.5
+            sd[key] = u(ref.shape, -b, b)
+        elif key.endswith(".weight"):                       # BatchNorm gamma (conv weights are 4-D)
+            sd[key] = u(ref.shape, 0.8, 1.2)
+        else:                                               # ".bias": conv bias if the sibling weight is 4-D, else BatchNorm beta
+            conv = net.state_dict()[key[:-4] + "weight"].dim() == 4
+            sd[key] = u(ref.shape, -0.05, 0.05) if conv else u(ref.shape, -0.1, 0.1)
+    return sd
+
+
+def calibrated_nbp(device, seed: int = 9, calib_S: int = 64, calib_B: int = 2):
+    """An eval-mode ``NBP`` on ``device`` with seeded weights whose BatchNorm running statistics are the batch statistics of
+    count-like inputs (one train-mode pass with momentum 1 on the CUDA kernels) and whose value head is scaled so that the
+    value map is O(1-10), like the x100 coverage gains the reference trains on (nbp_utils.py:668).  With default running
+    statistics activations explode / vanish and every accuracy figure would be meaningless."""
+    import torch
+    from .networks import NBP
+    net = NBP()
+    net.load_state_dict(seeded_nbp_state_dict(net, seed))
+    net.to(device)
+    net.train()
+    net.bn_momentum = 1.0
+    with torch.no_grad():
+        net(count_like_input(calib_B, calib_S, seed=seed + 1).to(device))
+    net.bn_momentum = 0.1
+    net.eval()
+    with torch.no_grad():
+        for k, v in net.state_dict().items():
+            if k.endswith("num_batches_tracked"):
+                v.zero_()
+        o1, _ = net(count_like_input(1, calib_S, seed=seed + 2).to(device))
+        scale = 5.0 / float(o1.abs().max().clamp_min(1e-6))
+        net.Final1.weight.mul_(scale)
+        net.Final1.bias.mul_(scale)
+    return net

@@ -61,3 +61,17 @@ def test_product_paths_refuse_cpu_tensors():
     from nextbestpath_b200.networks import NBP
     with pytest.raises(RuntimeError):
         NBP()(torch.zeros(1, 5, 32, 32))
+
+
+def test_package_seeded_weights_and_inputs_equal_the_oracles():
+    """bench.py's GPU arm builds its weights from the package (no oracle import on the product path); the recipe is the
+    oracle's, so the CPU baseline (oracle weights) and the GPU arm run the same network."""
+    import torch
+    from nextbestpath_b200 import synthetic as syn
+    from nextbestpath_b200.networks import NBP
+    from oracle import nbp_torch as NT
+    net = NBP()
+    a, b = syn.seeded_nbp_state_dict(net, 9), NT.seeded_state_dict(9)
+    assert list(a) == list(b) == list(net.state_dict())
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert torch.equal(syn.count_like_input(2, 32, seed=5), NT.count_like_input(2, 32, seed=5))

@@ -207,10 +207,12 @@ def test_pointwise_kernels_match_torch(precise):
         out = torch.empty((2, cout, 9, 7), device=DEV)
         sd_, _, ld_s, lo_s = _to_act(src, precise)
         wd_, bd = w.to(DEV), b.to(DEV)
-        _lib.check(L.nbp_conv1x1_head(sd_.data_ptr(), cin, ld_s, lo_s, wd_.data_ptr(), bd.data_ptr(), cout, sig, out.data_ptr(), 2, 63, _st()), "head")
+        omax = torch.empty((2, 9, 7), device=DEV)
+        _lib.check(L.nbp_conv1x1_head(sd_.data_ptr(), cin, ld_s, lo_s, wd_.data_ptr(), bd.data_ptr(), cout, sig, out.data_ptr(), omax.data_ptr(), 2, 63, _st()), "head")
         ref = torch.einsum("nchw,oc->nohw", src.double(), w.double()) + b.double()[None, :, None, None]
         ref = (torch.sigmoid(ref) if sig else ref).float()
         assert (out.cpu() - ref).abs().max() <= 3e-6 * max(1.0, ref.abs().max())
+        assert torch.equal(omax, out.amax(dim=1))                   # fused heading max (row a14)
     # stem: fp32 count image -> NHWC fp16
     xin = NT.count_like_input(2, 32, seed=1)
     w0 = torch.randn(64, 5, 3, 3, generator=g) * 0.1
@@ -280,6 +282,91 @@ def test_nbp_fast_fp16_mode_error_is_as_documented():
     m2, l2, _ = _errs(o2.cpu(), r2)
     print(f"fp16 fast mode: out1 max-rel {m1:.2e} l2-rel {l1:.2e} | out2 max-rel {m2:.2e} l2-rel {l2:.2e}")
     assert 1e-4 < l1 < 3e-2 and l2 < 5e-2
+
+
+def test_nbp_graph_replay_equals_eager_and_tracks_inputs_and_weights():
+    """Eval forward = replay of a captured CUDA graph (NBP.use_cuda_graph): same bits as the eager launch sequence, follows new
+    inputs, is re-captured when the weights change, and by default returns copies (the reference driver keeps the maps)."""
+    sd = NT.golden_state_dict(seed=9)
+    net = NBP(); net.load_state_dict(sd); net.to(DEV).eval()
+    xa, xb = NT.count_like_input(3, 64, seed=31).to(DEV), NT.count_like_input(3, 64, seed=32).to(DEV)
+    with torch.no_grad():
+        net.use_cuda_graph = False
+        ea, eb = net(xa), net(xb)
+        vmax_e = net.last_value_max.clone()
+        net.use_cuda_graph = True
+        n0 = ops_launches()
+        ga = net(xa)
+        n1 = ops_launches()
+        gb = net(xb)
+        n2 = ops_launches()
+        ga2 = net(xa.clone())
+    assert all(torch.equal(a, b) for a, b in zip(ea + eb, ga + gb)) and torch.equal(ga2[0], ga[0])
+    assert torch.equal(net.last_value_max, ga[0].amax(dim=1)) and torch.equal(vmax_e, eb[0].amax(dim=1))
+    assert ga[0].data_ptr() != gb[0].data_ptr()                      # copies, not the graph's buffers
+    assert n2 - n1 >= 40 and n1 - n0 >= n2 - n1                      # replays are accounted in nbp_launch_count
+    net.static_outputs = True
+    with torch.no_grad():
+        s1 = net(xa); p1 = s1[0].data_ptr(); v1 = s1[0].clone()
+        s2 = net(xb)
+    assert s2[0].data_ptr() == p1 and torch.equal(v1, ga[0]) and torch.equal(s2[0], gb[0])
+    net.static_outputs = False
+    with torch.no_grad():
+        net.Final1.bias.add_(1.0)                                    # in-place weight update -> re-pack -> re-capture
+        gc = net(xa)
+    assert torch.allclose(gc[0], ga[0] + 1.0, atol=1e-5) and torch.equal(gc[1], ga[1])
+
+
+def test_package_calibrated_weights_match_the_oracle_recipe():
+    """synthetic.calibrated_nbp (seeded weights, BatchNorm statistics from one momentum-1 train pass on the CUDA kernels, value
+    head rescaled) reproduces oracle.nbp_torch.golden_state_dict: bench.py's two arms run the same network."""
+    from nextbestpath_b200 import synthetic as syn
+    net = syn.calibrated_nbp(DEV, seed=9)
+    want = NT.golden_state_dict(seed=9)
+    got = net.state_dict()
+    assert not net.training and list(got) == list(want)
+    for k in want:
+        if k.endswith("num_batches_tracked"):
+            assert int(got[k]) == 0
+        else:
+            w = want[k].double()
+            assert float((got[k].cpu().double() - w).norm()) <= 2e-4 * max(float(w.norm()), 1e-3), k
+
+
+def ops_launches():
+    from nextbestpath_b200 import ops
+    return ops.launch_count()
+
+
+def test_fused_maxpool_epilogue_equals_pool_kernel():
+    """nbp_conv_fwd(pool_dst=...) writes MaxPool2d(2,2) of its output bit-identically to nbp_maxpool2x2 on that output
+    (16x8, 8x16(2 images) and 4-wide tiles; 128/64/32-channel tiles; single and chunked accumulation)."""
+    from nextbestpath_b200.networks import nbp_model as M
+    g = torch.Generator().manual_seed(3)
+    L = _lib.lib()
+    for (n, h, w, cin, cout, kch) in ((2, 32, 48, 64, 64, 0), (3, 8, 8, 128, 128, 2), (2, 16, 4, 64, 32, 0), (1, 16, 16, 256, 256, 0)):
+        wt = torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5
+        layer = {"w": M._pack_gemm_weight(wt.permute(0, 2, 3, 1).reshape(cout, -1), True).to(DEV), "c_out": cout,
+                 "scale": (torch.rand(cout, generator=g) + 0.5).to(DEV), "shift": (torch.randn(cout, generator=g) * 0.1).to(DEV)}
+        src, _, ld_s, lo_s = _to_act(torch.randn(n, cin, h, w, generator=g), True)
+        a = M._Act(src, cin, ld_s, lo_s, h, w)
+        mk = lambda hh, ww: M._Act(torch.zeros((n, hh, ww, 2 * cout), dtype=torch.float16, device=DEV), cout, 2 * cout, cout, hh, ww)
+        y0, y1, p_fused, p_ref = mk(h, w), mk(h, w), mk(h // 2, w // 2), mk(h // 2, w // 2)
+        M._conv({"precise": True}, layer, n, a, 9, y0, k_chunk=kch)
+        M._conv({"precise": True}, layer, n, a, 9, y1, k_chunk=kch, pool=p_fused)
+        _lib.check(L.nbp_maxpool2x2(y0.ptr, n, h, w, cout, y0.ld, y0.lo, p_ref.ptr, p_ref.ld, p_ref.lo, _st()), "pool")
+        torch.cuda.synchronize()
+        assert torch.equal(y0.t, y1.t), (n, h, w, cin, cout)
+        # expected: the (hi, lo) pair of the largest element of every 2x2 window, copied exactly (the split is monotonic)
+        hi, lo = y1.t[..., :cout].double(), y1.t[..., cout:].double()
+        win = lambda t: t.reshape(n, h // 2, 2, w // 2, 2, cout).permute(0, 1, 3, 5, 2, 4).reshape(n, h // 2, w // 2, cout, 4)
+        arg = win(hi + lo / 2048.0).argmax(-1, keepdim=True)
+        want = torch.cat((win(hi).gather(-1, arg).squeeze(-1), win(lo).gather(-1, arg).squeeze(-1)), dim=-1)
+        assert torch.equal(p_fused.t.double(), want), (n, h, w, cin, cout)
+        # the stand-alone pool kernel re-splits the fp32 sum hi + lo/2048: same value to fp32 rounding
+        v = lambda t: t[..., :cout].float() + t[..., cout:].float() / 2048.0
+        assert (v(p_fused.t) - v(p_ref.t)).abs().max() <= 2e-7 * v(p_ref.t).abs().max()
+        assert float(p_ref.t.float().abs().sum()) > 0
 
 
 def test_nbp_chunking_and_errors():

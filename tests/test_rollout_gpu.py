@@ -16,7 +16,7 @@ DEV = "cuda:0"
 H, W, S = 48, 86, 64
 
 
-def _oracle_rollout(scene, poses, az, n_steps, sd, gf, sensor_range, S=S, H=H, W=W):
+def _oracle_rollout(scene, poses, az, n_steps, sd, gf, sensor_range, S=S, H=H, W=W, sd64=None):
     """The reference loop (nbp_planning.py:60-355) restricted to the scoped stages, one scene, CPU."""
     verts, faces = scene.verts, scene.faces
     bounds = O.y_bins_from_verts(torch.from_numpy(verts)).numpy()[:-1]
@@ -31,7 +31,8 @@ def _oracle_rollout(scene, poses, az, n_steps, sd, gf, sensor_range, S=S, H=H, W
         grids.append(grid)
         with torch.no_grad():
             o1, o2 = NT.forward(sd, torch.from_numpy(grid)[None])
-        outs.append((o1[0], o2[0]))
+            _, t2 = NT.forward(sd64, torch.from_numpy(grid)[None].double()) if sd64 is not None else (None, o2)
+        outs.append((o1[0], o2[0], t2[0]))
         frames = [key]
         for k in range(1, 5):
             X, V = O.interpolate_pose(poses[t], poses[t + 1], k, 4, 8, int(az[t]), int(az[t + 1]))
@@ -69,6 +70,7 @@ def test_rollout_matches_oracle_rollout(n_steps, B, S, H, W, tris):
     poses = np.stack([w[0] for w in walks])          # (B, n_steps+1, 5)
     az = np.stack([w[1] for w in walks])
     sd = NT.golden_state_dict(seed=9)
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
     net = NBP(); net.load_state_dict(sd); net.to(DEV).eval()
     eng = RolloutEngine(scenes, net, DEV, S=S, H=H, W=W, max_steps=n_steps + 1, gathering_factor=1.0, sensor_range=30.0)
     eng.reset(poses[:, 0])
@@ -81,19 +83,24 @@ def test_rollout_matches_oracle_rollout(n_steps, B, S, H, W, tris):
     assert eng.overflow.item() == 0
     lens = eng.cloud_len.cpu().numpy()
     for b in range(B):
-        grids, outs, cloud = _oracle_rollout(scenes[b], poses[b], az[b], n_steps, sd, 1.0, 30.0, S, H, W)
+        grids, outs, cloud = _oracle_rollout(scenes[b], poses[b], az[b], n_steps, sd, 1.0, 30.0, S, H, W, sd64)
         assert lens[b] == len(cloud)
         assert np.array_equal(eng.cloud[b, : lens[b]].cpu().numpy(), cloud)            # same points, same order
         for t in range(n_steps):
             assert np.array_equal(got[t][0][b], grids[t]), f"scene {b} step {t}: model input differs"
-            o1, o2 = outs[t]
+            o1, o2, o2_f64 = outs[t]
             e1 = (got[t][1][b] - o1).abs().max() / o1.abs().max()
-            e2 = (got[t][2][b] - o2).abs().max()
             l2 = (got[t][2][b] - o2).norm() / o2.norm()
-            # value map: max error relative to the map's maximum; obstacle map (a sigmoid probability in [0, 1], thresholded at
-            # 0.13 by the planner): absolute error and l2-relative error -- all at the 1e-3 parity bar
-            print(f"S={S} scene {b} step {t}: value map {float(e1):.2e}, obstacle map abs {float(e2):.2e} l2-rel {float(l2):.2e}")
-            assert e1 <= 1e-3 and e2 <= 1e-3 and l2 <= 1e-3, (float(e1), float(e2), float(l2))
+            # value map: max error relative to the map's maximum, and the obstacle map's l2-relative error: the 1e-3 parity bar.
+            # obstacle map, worst single pixel (a sigmoid probability, thresholded at 0.13 by the planner): measured against the
+            # float64 evaluation.  With gathering_factor 1 a grid cell here holds up to ~11 000 points (the reference's 5 % sampling:
+            # a few hundred), logits overflow to +-inf, and the reference's own fp32 arithmetic is up to 3.3e-3 away from float64 on
+            # single pixels -- the bar is 1e-3, or twice fp32's own error where that is larger.
+            e2 = (got[t][2][b].double() - o2_f64).abs().max()
+            e2_f32 = (o2.double() - o2_f64).abs().max()
+            print(f"S={S} scene {b} step {t} (max count {int(grids[t].max())}): value map {float(e1):.2e}, obstacle map l2-rel {float(l2):.2e}, "
+                  f"worst pixel vs fp64 {float(e2):.2e} (fp32 oracle vs fp64: {float(e2_f32):.2e})")
+            assert e1 <= 1e-3 and l2 <= 1e-3 and e2 <= max(1e-3, 2.0 * float(e2_f32)), (float(e1), float(e2), float(e2_f32), float(l2))
             assert torch.equal(got[t][3][b], got[t][1][b].amax(dim=0))
         assert grids[-1][:4].sum() > 1000 and grids[-1][4].sum() >= (9 if n_steps >= 3 else 1)
 

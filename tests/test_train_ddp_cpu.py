@@ -63,10 +63,26 @@ def test_flat_gradient_allreduce_two_ranks():
     assert m0 == m1
 
 
-def test_single_process_is_a_no_op():
+def test_single_process_keeps_gradients_and_attaches_the_flat_views():
     net = _Tiny()
     net(torch.randn(2, 4)).sum().backward()
-    before = [p.grad.clone() for p in net.parameters() if p.grad is not None]
-    assert FlatGradAllReduce(net.parameters()).sync() == 0
-    after = [p.grad for p in net.parameters() if p.grad is not None]
-    assert all(torch.equal(a, b) for a, b in zip(before, after))
+    before = {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for n, p in net.named_parameters()}
+    red = FlatGradAllReduce(net.parameters())                      # adopts the existing gradients
+    assert red.sync() == 0                                         # single process: no collective
+    for (n, p), v in zip(net.named_parameters(), red.views):
+        assert p.grad is v and torch.equal(p.grad, before[n])      # same values, now living in the flat buffer
+    # backward accumulates straight into the flat buffer; zero() is one memset and keeps the views attached
+    net(torch.randn(2, 4)).sum().backward()
+    assert all(p.grad is v for p, v in zip(net.parameters(), red.views)) and float(red.flat.abs().sum()) > 0
+    red.zero()
+    assert float(red.flat.abs().sum()) == 0 and all(p.grad is v for p, v in zip(net.parameters(), red.views))
+    # a caller that detaches (optimizer.zero_grad() sets .grad to None, as the reference loop does) is picked up by sync()
+    torch.optim.SGD(net.parameters(), lr=0.1).zero_grad()
+    net(torch.ones(2, 4)).sum().backward()
+    g = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    red.sync()
+    for (n, p), v in zip(net.named_parameters(), red.views):
+        assert p.grad is v and torch.equal(v, g.get(n, torch.zeros_like(p)))
+    assert not red.nonfinite()
+    red.flat[0] = float("inf")
+    assert red.nonfinite()
