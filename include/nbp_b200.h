@@ -133,8 +133,12 @@ int nbp_point_cells(const float* points_2d, int64_t n, int S0, int S1, float ran
  * offsets let a producer write straight into a concatenation buffer (torch.cat at :128,133,...).
  */
 typedef struct nbp_conv_desc {
-    int precise;                           /* 1: fp16x2 split format (hi plane + lo*2048 plane), fp32-grade results;
-                                              0: single fp16 plane */
+    int precise;                           /* numeric mode = format of the SOURCE tensors and of the weights:
+                                              0: single fp16 plane;
+                                              1: fp16x2 split format (hi plane + lo*2048 plane), 3 tensor passes, fp32-grade results;
+                                              2: fp16 hi plane + an e4m3 pair plane (per 64-channel group: 64 bytes e4m3(x), then 64 bytes
+                                                 e4m3((x - hi) * 2048)); the hi product runs on the fp16 pipe, both correction products as one
+                                                 e4m3 reduction (kind::f8f6f4, 2x rate): 2 pass-equivalents, ~15-bit operands */
     const void* src0; int c0; int ld0; int lo0;  /* NHWC fp16: c0 channels per pixel, pixel stride ld0 elements; with
                                               precise, the lo plane starts lo0 elements after src0 */
     const void* src1; int c1; int ld1; int lo1;  /* optional second source, concatenated after src0 along channels */
@@ -146,7 +150,8 @@ typedef struct nbp_conv_desc {
                                               is [n][2h][2w]; weight holds 4 blocks (parity = py*2+px), each [c_out][4 taps][c_in] packed
                                               like a normal weight; tap t reads source (y + t/2 - 1 + py, x + t%2 - 1 + px). 2.25x fewer MACs. */
     const void* weight;                    /* fp16 [c_out][taps][c0+c1] (K-major); tap = ky*3+kx.  precise: per tile of
-                                              BN = 128|64|32 output channels (largest dividing c_out) BN hi rows then BN lo rows */
+                                              BN = 128|64|32 output channels (largest dividing c_out) BN hi rows then BN lo rows; mode 2: the
+                                              lo rows hold, per 64-element K slice, 64 bytes e4m3(W_lo*2048*s) then 64 bytes e4m3(W_hi*s) */
     int c_out;                             /* multiple of 32 */
     const float* scale; const float* shift;/* [c_out] fp32: y = acc*scale + shift */
     int relu;
@@ -157,6 +162,11 @@ typedef struct nbp_conv_desc {
                                               fp32 accumulator before the partial sum is folded into fp32 round-to-nearest registers;
                                               0 = default (8).  Smaller = more accurate, slower (measured: 8 -> 3.6e-5 network error,
                                               2 -> floor of the 22-bit operands, -10 % throughput) */
+    int dst_fmt;                           /* precise != 0, out_f32 == 0: second-plane format WRITTEN to dst: 0 = the mode's own, 1 = fp16 lo*2048 (consumers run
+                                              mode 1), 2 = e4m3 pair plane (consumers run mode 2; dst_c_off % 32 == 0, dst_lo_off % 64 == 0).
+                                              A mode-1 layer may write format 2 and vice versa: the network mixes both (nbp_model.py) */
+    int pool_fmt;                          /* same for pool_dst */
+    float w_lo_scale;                      /* mode 2: 1 / (2048 s), s = the power of two the e4m3 weight rows were scaled by */
     void* pool_dst; int pool_ld; int pool_lo_off; /* optional (NULL = off): ALSO write nn.MaxPool2d(2,2) of the output (nbp_model.py:68,113-121)
                                               as an NHWC fp16 tensor [n][h/2][w/2][pool_ld] (lo plane pool_lo_off elements after the hi
                                               channels), fused into the epilogue: the encoder needs both the skip tensor and its pooled
@@ -166,7 +176,8 @@ typedef struct nbp_conv_desc {
 /* tcgen05/TMEM/TMA implicit-GEMM convolution: conv_block / up_conv / Attention_block W_g,W_x (nbp_model.py:8-62) */
 int nbp_conv_fwd(const nbp_conv_desc* desc, void* stream);
 /* The pointwise kernels below take, for every NHWC fp16 tensor, the pixel stride `ld` (elements) and the
- * offset `lo` of the lo plane of the fp16x2 format (0 = single-plane fp16 tensor). */
+ * offset `lo` of the second plane (0 = single-plane fp16 tensor).  `fmt` (nbp_conv_first, nbp_att_gate, nbp_conv1x1_head) selects
+ * the second-plane format of ALL tensors of the call: 1 = fp16 (x - hi) * 2048, 2 = the e4m3 pair plane of nbp_conv_desc mode 2. */
 /* Measurement aid for bench.py (not part of the data path): between _begin and _end every conv_gemm launch is
  * bracketed by CUDA events on its stream; _end waits for them and returns the summed device time, the summed
  * ALGORITHMIC flops (2*M*N*K of the convolution, independent of the numeric mode) and the launch count.
@@ -177,7 +188,7 @@ int nbp_conv_profile_end(double* total_ms_host, double* total_flops_host, uint64
  * (tap-major, then input channel), c_out = 64; fused affine + optional ReLU (nbp_model.py:11-13).  Train mode calls it
  * with scale 1 / shift bias / relu 0 to get the raw pre-BatchNorm tensor. */
 int nbp_conv_first(const float* x, int n, int c_in, int h, int w, const float* weight, const float* scale,
-                   const float* shift, int c_out, int relu, void* dst, int dst_ld, int dst_lo, void* stream);
+                   const float* shift, int c_out, int relu, void* dst, int dst_ld, int dst_lo, int fmt, void* stream);
 /* nn.MaxPool2d(2,2) (nbp_model.py:68) and nn.Upsample(scale_factor=2) nearest (:27) on NHWC fp16 */
 int nbp_maxpool2x2(const void* src, int n, int h, int w, int c, int ld_src, int lo_src, void* dst, int ld_dst, int lo_dst, void* stream);
 int nbp_upsample2x(const void* src, int n, int h, int w, int c, int ld_src, int lo_src, void* dst, int ld_dst, int lo_dst, void* stream);
@@ -185,12 +196,12 @@ int nbp_upsample2x(const void* src, int n, int h, int w, int c, int ld_src, int 
  * a [npix] x f_int = relu(BN(W_g g) + BN(W_x x)); x [npix] x f_l; dst written at channel dst_c_off */
 int nbp_att_gate(const void* a, int f_int, int ld_a, int lo_a, const void* x, int f_l, int ld_x, int lo_x,
                  const float* w_psi, float psi_scale, float psi_shift,
-                 void* dst, int dst_ld, int dst_c_off, int dst_lo, int64_t npix, void* stream);
+                 void* dst, int dst_ld, int dst_c_off, int dst_lo, int64_t npix, int fmt, void* stream);
 /* Final1 (256->8) and Final2 (64->1, sigmoid) (nbp_model.py:89,106-108): NHWC fp16 in, NCHW fp32 out [n,c_out,hw];
  * weight fp32 [c_out][c_in], c_out in {1, 8}.  dst_max (optional, NULL = off): [n,hw] fp32 = max over the c_out channels, the
  * heading read-out `torch.max(predicted_value_map, dim=1)` of next_best_path/testers/nbp_planning.py:193 fused into the head */
 int nbp_conv1x1_head(const void* src, int c_in, int ld_src, int lo_src, const float* weight, const float* bias, int c_out,
-                     int sigmoid, float* dst, float* dst_max, int n, int64_t hw, void* stream);
+                     int sigmoid, float* dst, float* dst_max, int n, int64_t hw, int fmt, void* stream);
 
 /* ------------------------------------------------------------------------------------------ a11 (train mode), a13
  * Train-mode BatchNorm2d (batch statistics, running-stat update: momentum 0.1, unbiased running variance, eps 1e-5 --

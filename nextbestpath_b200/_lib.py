@@ -41,18 +41,19 @@ class ConvDesc(C.Structure):
                 ("src1", _p), ("c1", _i), ("ld1", _i), ("lo1", _i),
                 ("n", _i), ("h", _i), ("w", _i), ("taps", _i), ("up2x", _i), ("weight", _p), ("c_out", _i),
                 ("scale", _p), ("shift", _p), ("relu", _i), ("dst", _p), ("dst_ld", _i), ("dst_c_off", _i),
-                ("dst_lo_off", _i), ("out_f32", _i), ("k_chunk", _i), ("pool_dst", _p), ("pool_ld", _i), ("pool_lo_off", _i)]
+                ("dst_lo_off", _i), ("out_f32", _i), ("k_chunk", _i), ("dst_fmt", _i), ("pool_fmt", _i), ("w_lo_scale", _f),
+                ("pool_dst", _p), ("pool_ld", _i), ("pool_lo_off", _i)]
 
 
 SIGNATURES.update({
     "nbp_conv_fwd": (_i, [C.POINTER(ConvDesc), _p]),
     "nbp_conv_profile_begin": (_i, [_i]),
     "nbp_conv_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
-    "nbp_conv_first": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p, _i, _i, _p]),
+    "nbp_conv_first": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _p]),
     "nbp_maxpool2x2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     "nbp_upsample2x": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
-    "nbp_att_gate": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p, _f, _f, _p, _i, _i, _i, _l, _p]),
-    "nbp_conv1x1_head": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _l, _p]),
+    "nbp_att_gate": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p, _f, _f, _p, _i, _i, _i, _l, _i, _p]),
+    "nbp_conv1x1_head": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _l, _i, _p]),
 })
 
 _d = C.c_double

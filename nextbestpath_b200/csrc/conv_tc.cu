@@ -12,6 +12,14 @@
 //       and the epilogue returns acc_hi + acc_lo/2048.  Measured on the BN-calibrated parity weights this
 //       is 7e-6 relative to the fp32 reference (plain fp16 or tf32 storage: 7e-3, bf16: 5e-2), which is what
 //       the "value maps within 1e-3 of fp32" bar needs ("numeric format").  3 MMA passes.
+//   MODE 2 "fp16+e4m3": the same hi planes, but both correction products run on the 8-bit floating-point pipe (kind::f8f6f4,
+//       twice the MAC rate).  The second plane of an activation holds, per 64-channel group, 64 bytes e4m3(x) followed by
+//       64 bytes e4m3((x - hi) * 2048); the matching weight rows hold e4m3(W_lo * 2048 * s) followed by e4m3(W_hi * s) (s = a
+//       per-layer power of two).  ONE K = 128 fp8 reduction per 64-channel slice then yields
+//           acc_lo = A_hi8 * W_lo8  +  A_lo8 * W_hi8
+//       and the epilogue returns acc_hi + acc_lo / (2048 s).  Operands keep ~15 bits instead of 22 and a slice costs
+//       4 + 4 half-rate-equivalent UMMAs instead of 12: 2/3 of the tensor time.  Measured network error with the five most
+//       sensitive encoder layers kept in fp16x2: 1.0-1.3e-4 (value map) / 2.4-4.8e-4 (obstacle map), bar 1e-3.
 //   PRECISE = false "fp16": single fp16 plane, 1 MMA pass; 7e-3 relative on the same weights.
 // Layout: activations NHWC fp16, channel counts multiples of 64; PRECISE tensors carry a second plane
 // (lo * 2048) `lo_off` elements after the first.  Weights fp16 [c_out][taps][c_in] (K-major).
@@ -40,6 +48,13 @@ namespace nbp {
 
 using namespace tc;
 
+// two floats -> packed e4m3x2 (round to nearest even, saturating at +-448); low byte = first value
+__device__ __forceinline__ uint32_t e4m3x2(float a, float b) {
+    uint16_t r;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %2, %1;" : "=h"(r) : "f"(a), "f"(b));
+    return (uint32_t)r;
+}
+
 static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_K = 64;                         // fp16 elements = one 128-byte swizzle row
 static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;     // one plane of a plain 128-pixel A block
@@ -55,6 +70,8 @@ struct ConvKParams {
     int m_tiles, n_tiles;
     int taps, kc0, kc1;
     int lo0, lo1;                       // element offset of the lo plane inside the tensor maps (PRECISE)
+    float lo_scale;                     // acc = acc_hi + acc_lo * lo_scale (1/2048 for fp16x2, 1/(2048 s) for fp16+e4m3)
+    int dst_fmt, pool_fmt;              // second-plane format written by the epilogue: 1 = fp16 lo*2048, 2 = e4m3 pair (MODE 2 consumers)
     int out_f32;                        // 1: the destination is plain fp32 NHWC (gradients), no fp16 planes
     int kchunk;                         // K stages accumulated inside TMEM before the partial sum is folded into fp32
                                         // registers (round-to-nearest); the tensor core's own accumulator truncates
@@ -71,8 +88,9 @@ struct ConvKParams {
     __half* pool; int pool_ld, pool_lo_off;   // optional second output: the 2x2 max-pooled activation [n][h/2][w/2] (fused nn.MaxPool2d)
 };
 
-template <int BLOCK_N, bool PRECISE, int HALO>     // HALO = 0: plain stages; 2 | 3: halo stages carrying that many taps
+template <int BLOCK_N, int MODE, int HALO>     // MODE 0 fp16 | 1 fp16x2 | 2 fp16+e4m3; HALO = 0: plain stages; 2 | 3: halo stages carrying that many taps
 struct ConvCfg {
+    static constexpr bool PRECISE = MODE != 0;
     static constexpr int PLANES = PRECISE ? 2 : 1;
     static constexpr int A_PLANE = HALO ? A_HALO_BYTES : A_STAGE_BYTES;
     static constexpr int A_BYTES = PLANES * A_PLANE;                      // A_hi [, A_lo]
@@ -89,12 +107,14 @@ struct ConvCfg {
     static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
 };
 
-template <int BLOCK_N, bool PRECISE, int HALO>
+template <int BLOCK_N, int MODE, int HALO>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
               const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
-    using Cfg = ConvCfg<BLOCK_N, PRECISE, HALO>;
+    using Cfg = ConvCfg<BLOCK_N, MODE, HALO>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr bool PRECISE = MODE != 0;
+    constexpr bool FP8 = MODE == 2;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -200,23 +220,36 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                             const uint64_t adesc = umma_desc_kmajor_sw128(a_addr + (uint32_t)((row0 + j) * p.aoff_step));
                             const uint64_t alo = umma_desc_kmajor_sw128(a_addr + (uint32_t)((row0 + j) * p.aoff_step) + Cfg::A_PLANE);
                             const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr + (uint32_t)(j * Cfg::B_TILE_BYTES));
+                            const uint64_t blo = umma_desc_kmajor_sw128(b_addr + (uint32_t)(j * Cfg::B_TILE_BYTES + BLOCK_N * BLOCK_K * 2));
 #pragma unroll
                             for (int k = 0; k < BLOCK_K / 16; ++k) {
-                                umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_main, (ks > ks0 || j > 0 || k > 0) ? 1u : 0u);
-                                if (PRECISE) umma_f16(d_tmem + (uint32_t)BLOCK_N, alo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, 1u);
+                                const uint32_t accum = (ks > ks0 || j > 0 || k > 0) ? 1u : 0u;
+                                if (FP8) {
+                                    umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, accum);
+                                    umma_f8(d_tmem + (uint32_t)BLOCK_N, alo + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), idesc_lo, accum);
+                                } else {
+                                    umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_main, accum);
+                                    if (PRECISE) umma_f16(d_tmem + (uint32_t)BLOCK_N, alo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, 1u);
+                                }
                             }
                         }
                     } else {
                     const uint64_t adesc = umma_desc_kmajor_sw128(a_addr);
                     const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr);
+                    const uint64_t alo = umma_desc_kmajor_sw128(a_addr + A_STAGE_BYTES);
+                    const uint64_t blo = umma_desc_kmajor_sw128(b_addr + BLOCK_N * BLOCK_K * 2);     // the e4m3 weight rows (MODE 2)
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; ++k) {
-                        // +32 bytes (16 fp16) along K inside the 128-byte swizzle row: +2 in the encoded address
-                        umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_main, (ks > ks0 || k > 0) ? 1u : 0u);
-                        if (PRECISE) {
+                        // +32 bytes along K inside the 128-byte swizzle row (16 fp16 or 32 e4m3): +2 in the encoded address
+                        const uint32_t accum = (ks > ks0 || k > 0) ? 1u : 0u;
+                        if (FP8) {
+                            // hi product on the fp16 pipe, both corrections as one K = 128 e4m3 reduction ([A_hi8 | A_lo8] . [W_lo8 ; W_hi8])
+                            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, accum);
+                            umma_f8(d_tmem + (uint32_t)BLOCK_N, alo + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), idesc_lo, accum);
+                        } else {
+                            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_main, accum);
                             // A_lo * W_hi accumulates into the acc_lo columns that the UMMA above just wrote (in-order pipe)
-                            const uint64_t alo = umma_desc_kmajor_sw128(a_addr + A_STAGE_BYTES);
-                            umma_f16(d_tmem + (uint32_t)BLOCK_N, alo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, 1u);
+                            if (PRECISE) umma_f16(d_tmem + (uint32_t)BLOCK_N, alo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, 1u);
                         }
                     }
                     }
@@ -262,7 +295,6 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             asm volatile("bar.sync 1, 128;" ::: "memory");
 
             const size_t opix = (size_t)((size_t)nn * oh + oy) * ow + ox;
-            __half* orow = p.dst + opix * p.dst_ld + p.dst_c_off + n_tile * BLOCK_N;
             float* orow_f = reinterpret_cast<float*>(p.dst) + opix * p.dst_ld + p.dst_c_off + n_tile * BLOCK_N;
 
             // affine + activation + store of 32 consecutive output channels held as fp32 in v[]
@@ -289,29 +321,42 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                     if (p.relu) t = fmaxf(t, 0.0f);
                     a[j] = fminf(fmaxf(t, -65504.0f), 65504.0f);
                 }
-                // fp32 -> fp16 planes (hi [, (x - hi) * 2048]) -> 16-byte stores
-                auto split_store = [&](__half* row, int lo_off, const float* x) {
+                // fp32 -> hi plane (fp16) + second plane -> 16-byte stores.  `pix` = first element of the pixel, `ch` = channel of x[0]
+                // inside the pixel, `lo_off` = offset of the second plane; fmt 1: fp16 (x - hi) * 2048 at the same channel index,
+                // fmt 2: per 64-channel group 64 bytes e4m3(x) then 64 bytes e4m3((x - hi) * 2048)
+                auto split_store = [&](__half* pix, int ch, int lo_off, int fmt, const float* x) {
                     uint32_t packed[16], packed_lo[16];
+                    uint32_t p8h[8], p8l[8];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const __half2 h = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
                         packed[j] = *reinterpret_cast<const uint32_t*>(&h);
                         if (PRECISE) {
                             const float2 hf = __half22float2(h);
-                            const __half2 l = __floats2half2_rn((x[2 * j] - hf.x) * 2048.0f, (x[2 * j + 1] - hf.y) * 2048.0f);
+                            const float r0 = (x[2 * j] - hf.x) * 2048.0f, r1 = (x[2 * j + 1] - hf.y) * 2048.0f;
+                            const __half2 l = __floats2half2_rn(r0, r1);
                             packed_lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+                            const uint32_t qh = e4m3x2(x[2 * j], x[2 * j + 1]), ql = e4m3x2(r0, r1);
+                            if (j & 1) { p8h[j >> 1] |= qh << 16; p8l[j >> 1] |= ql << 16; } else { p8h[j >> 1] = qh; p8l[j >> 1] = ql; }
                         }
                     }
-                    uint4* o = reinterpret_cast<uint4*>(row);
+                    uint4* o = reinterpret_cast<uint4*>(pix + ch);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) o[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
                     if (PRECISE) {
-                        uint4* ol = reinterpret_cast<uint4*>(row + lo_off);
+                        if (fmt == 2) {
+                            uint8_t* g = reinterpret_cast<uint8_t*>(pix + lo_off) + (ch >> 6) * 128 + (ch & 63);
+                            uint4* oh = reinterpret_cast<uint4*>(g); uint4* ol = reinterpret_cast<uint4*>(g + 64);
+                            oh[0] = make_uint4(p8h[0], p8h[1], p8h[2], p8h[3]); oh[1] = make_uint4(p8h[4], p8h[5], p8h[6], p8h[7]);
+                            ol[0] = make_uint4(p8l[0], p8l[1], p8l[2], p8l[3]); ol[1] = make_uint4(p8l[4], p8l[5], p8l[6], p8l[7]);
+                        } else {
+                            uint4* ol = reinterpret_cast<uint4*>(pix + ch + lo_off);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) ol[j] = make_uint4(packed_lo[4 * j], packed_lo[4 * j + 1], packed_lo[4 * j + 2], packed_lo[4 * j + 3]);
+                            for (int j = 0; j < 4; ++j) ol[j] = make_uint4(packed_lo[4 * j], packed_lo[4 * j + 1], packed_lo[4 * j + 2], packed_lo[4 * j + 3]);
+                        }
                     }
                 };
-                if (valid) split_store(orow + c * 32, p.dst_lo_off, a);
+                if (valid) split_store(p.dst + opix * p.dst_ld, p.dst_c_off + n_tile * BLOCK_N + c * 32, p.dst_lo_off, p.dst_fmt, a);
                 if (p.pool) {
                     // fused nn.MaxPool2d(2,2): the 2x2 window of a pixel lives in lanes {l, l^1, l^tw, l^(tw+1)} of this warp (tile rows
                     // are tw <= 16 pixels wide and a warp holds 32 consecutive tile pixels); max commutes with the monotonic hi/lo split
@@ -322,7 +367,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                     }
                     if (valid && !((wi | hi) & 1)) {
                         const size_t ppix = ((size_t)nn * (p.h >> 1) + (y >> 1)) * (size_t)(p.w >> 1) + (x >> 1);
-                        split_store(p.pool + ppix * p.pool_ld + n_tile * BLOCK_N + c * 32, p.pool_lo_off, a);
+                        split_store(p.pool + ppix * p.pool_ld, n_tile * BLOCK_N + c * 32, p.pool_lo_off, p.pool_fmt, a);
                     }
                 }
             };
@@ -335,7 +380,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                     tmem_ld_32x32(t_row + (uint32_t)(BLOCK_N + c * 32), vl);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) out[j] = fmaf(__uint_as_float(vl[j]), 1.0f / 2048.0f, __uint_as_float(v[j]));
+                    for (int j = 0; j < 32; ++j) out[j] = fmaf(__uint_as_float(vl[j]), p.lo_scale, __uint_as_float(v[j]));
                 } else {
                     tmem_ld_wait();
 #pragma unroll
@@ -450,12 +495,12 @@ static ConvProfile g_prof;
 static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 static int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
 
-template <int BLOCK_N, bool PRECISE, int HALO = 0>
+template <int BLOCK_N, int MODE, int HALO = 0>
 static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvKParams& kp, int sms, cudaStream_t st) {
-    using Cfg = ConvCfg<BLOCK_N, PRECISE, HALO>;
+    using Cfg = ConvCfg<BLOCK_N, MODE, HALO>;
     static bool attr_set = false;
     if (!attr_set) {
-        int rc = check_cuda(cudaFuncSetAttribute(conv_gemm_f16<BLOCK_N, PRECISE, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES),
+        int rc = check_cuda(cudaFuncSetAttribute(conv_gemm_f16<BLOCK_N, MODE, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES),
                             "cudaFuncSetAttribute(conv_gemm_f16)");
         if (rc) return rc;
         attr_set = true;
@@ -465,7 +510,7 @@ static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
     const bool prof = g_prof.enabled && g_prof.used + 2 <= g_prof.ev.size();
     if (g_prof.enabled && !prof) ++g_prof.dropped;
     if (prof) cudaEventRecord(g_prof.ev[g_prof.used], st);
-    conv_gemm_f16<BLOCK_N, PRECISE, HALO><<<grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b, kp);
+    conv_gemm_f16<BLOCK_N, MODE, HALO><<<grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b, kp);
     if (prof) {
         cudaEventRecord(g_prof.ev[g_prof.used + 1], st);
         g_prof.used += 2;
@@ -489,7 +534,16 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     if (d->n <= 0 || d->h <= 0 || d->w <= 0) return invalid("nbp_conv_fwd: bad image dims n=%d h=%d w=%d", d->n, d->h, d->w);
     if (d->c0 <= 0 || d->c0 % BLOCK_K || d->c1 < 0 || d->c1 % BLOCK_K || (d->c1 > 0 && !d->src1))
         return invalid("nbp_conv_fwd: source channels must be positive multiples of 64 (c0=%d c1=%d)", d->c0, d->c1);
+    if (d->precise < 0 || d->precise > 2) return invalid("nbp_conv_fwd: precise must be 0 (fp16), 1 (fp16x2) or 2 (fp16 + e4m3 corrections), got %d", d->precise);
     const bool precise = d->precise != 0;
+    const bool fp8 = d->precise == 2;
+    if (fp8 && d->out_f32) return invalid("nbp_conv_fwd: the fp16+e4m3 mode has no fp32 output (it is an eval-path format)");
+    if (fp8 && !(d->w_lo_scale > 0.0f)) return invalid("nbp_conv_fwd: precise = 2 needs w_lo_scale = 1 / (2048 s) > 0");
+    const int dst_fmt = d->dst_fmt ? d->dst_fmt : d->precise, pool_fmt = d->pool_fmt ? d->pool_fmt : d->precise;   // 0 = the mode's own format
+    if (precise && !d->out_f32 && dst_fmt != 1 && dst_fmt != 2) return invalid("nbp_conv_fwd: dst_fmt must be 0 (as the sources), 1 (fp16 lo plane) or 2 (e4m3 pair plane)");
+    if (precise && d->pool_dst && pool_fmt != 1 && pool_fmt != 2) return invalid("nbp_conv_fwd: pool_fmt must be 0, 1 or 2");
+    if (precise && ((dst_fmt == 2 && (d->dst_c_off % 32 || d->dst_lo_off % 64)) || (d->pool_dst && pool_fmt == 2 && d->pool_lo_off % 64)))
+        return invalid("nbp_conv_fwd: e4m3 pair planes need 64-channel aligned plane offsets");
     const int span0 = precise ? d->lo0 + d->c0 : d->c0, span1 = precise ? d->lo1 + d->c1 : d->c1;
     if (precise && (d->lo0 < d->c0 || d->lo0 % 8 || (d->c1 > 0 && (d->lo1 < d->c1 || d->lo1 % 8)) ||
                     (!d->out_f32 && (d->dst_lo_off < d->c_out || d->dst_lo_off % 8))))
@@ -513,6 +567,8 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     kp.m_tiles = kp.tiles_x * kp.tiles_y * kp.tiles_n; kp.n_tiles = d->c_out / block_n;
     kp.taps = d->taps; kp.kc0 = d->c0 / BLOCK_K; kp.kc1 = d->c1 / BLOCK_K;
     kp.lo0 = d->lo0; kp.lo1 = d->lo1;
+    kp.lo_scale = fp8 ? d->w_lo_scale : 1.0f / 2048.0f;
+    kp.dst_fmt = dst_fmt; kp.pool_fmt = pool_fmt;
     kp.up2x = d->up2x ? 1 : 0;
     kp.out_f32 = d->out_f32 ? 1 : 0;
     // ---- vertical halo reuse (64- and 32-channel tiles, whose K steps are too short to hide the operand latency): tiles inside one
@@ -574,19 +630,28 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
         if (rc) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (fp8) {
+        switch (block_n) {
+            case 128: return launch_conv<128, 2>(a0, a1, b, kp, sms, st);
+            case 64:  return !halo ? launch_conv<64, 2>(a0, a1, b, kp, sms, st)
+                             : d->up2x ? launch_conv<64, 2, 2>(a0, a1, b, kp, sms, st) : launch_conv<64, 2, 3>(a0, a1, b, kp, sms, st);
+            default:  return !halo ? launch_conv<32, 2>(a0, a1, b, kp, sms, st)
+                             : d->up2x ? launch_conv<32, 2, 2>(a0, a1, b, kp, sms, st) : launch_conv<32, 2, 3>(a0, a1, b, kp, sms, st);
+        }
+    }
     if (precise) {
         switch (block_n) {
-            case 128: return launch_conv<128, true>(a0, a1, b, kp, sms, st);
-            case 64:  return !halo ? launch_conv<64, true>(a0, a1, b, kp, sms, st)
-                             : d->up2x ? launch_conv<64, true, 2>(a0, a1, b, kp, sms, st) : launch_conv<64, true, 3>(a0, a1, b, kp, sms, st);
-            default:  return !halo ? launch_conv<32, true>(a0, a1, b, kp, sms, st)
-                             : d->up2x ? launch_conv<32, true, 2>(a0, a1, b, kp, sms, st) : launch_conv<32, true, 3>(a0, a1, b, kp, sms, st);
+            case 128: return launch_conv<128, 1>(a0, a1, b, kp, sms, st);
+            case 64:  return !halo ? launch_conv<64, 1>(a0, a1, b, kp, sms, st)
+                             : d->up2x ? launch_conv<64, 1, 2>(a0, a1, b, kp, sms, st) : launch_conv<64, 1, 3>(a0, a1, b, kp, sms, st);
+            default:  return !halo ? launch_conv<32, 1>(a0, a1, b, kp, sms, st)
+                             : d->up2x ? launch_conv<32, 1, 2>(a0, a1, b, kp, sms, st) : launch_conv<32, 1, 3>(a0, a1, b, kp, sms, st);
         }
     }
     switch (block_n) {
-        case 128: return launch_conv<128, false>(a0, a1, b, kp, sms, st);
-        case 64:  return launch_conv<64, false>(a0, a1, b, kp, sms, st);
-        default:  return launch_conv<32, false>(a0, a1, b, kp, sms, st);
+        case 128: return launch_conv<128, 0>(a0, a1, b, kp, sms, st);
+        case 64:  return launch_conv<64, 0>(a0, a1, b, kp, sms, st);
+        default:  return launch_conv<32, 0>(a0, a1, b, kp, sms, st);
     }
 }
 

@@ -12,17 +12,40 @@
 
 namespace nbp {
 
-// Activation format helpers.  A tensor is NHWC fp16; in the fp16x2 ("precise") format each pixel carries a
-// second plane holding (value - hi) * 2048, `lo` elements after the first (lo == 0: single plane).
+// Activation format helpers.  A tensor is NHWC fp16; `pix` points at the first element of a pixel, `ch` is a channel index
+// (multiple of 8) and `lo` the offset of the pixel's second plane (0: single fp16 plane).  Second-plane formats (`fmt`):
+//   1  fp16x2: fp16 (value - hi) * 2048 at the same channel index
+//   2  e4m3 pair: per 64-channel group 64 bytes e4m3(value) followed by 64 bytes e4m3((value - hi) * 2048) -- the operand layout of
+//      the conv kernel's fp16 + e4m3 mode; the value read back is hi + e4m3_lo / 2048 (~15 bits)
 static constexpr float LO_SCALE = 2048.0f;
 
-__device__ __forceinline__ void load8(const __half* p, int lo, float* f) {
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+__device__ __forceinline__ uint32_t e4m3x2(float a, float b) {           // low byte = a; round to nearest even, saturating
+    uint16_t r;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %2, %1;" : "=h"(r) : "f"(a), "f"(b));
+    return (uint32_t)r;
+}
+__device__ __forceinline__ float2 e4m3x2_to_float2(uint32_t v) {
+    uint32_t h2;
+    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"((uint16_t)v));
+    return __half22float2(*reinterpret_cast<const __half2*>(&h2));
+}
+
+__device__ __forceinline__ void load8(const __half* pix, int ch, int lo, int fmt, float* f) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(pix + ch));
     const __half2* hq = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
     for (int j = 0; j < 4; ++j) { const float2 t = __half22float2(hq[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
-    if (lo) {
-        const uint4 r = __ldg(reinterpret_cast<const uint4*>(p + lo));
+    if (lo && fmt == 2) {
+        const uint2 r = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(pix + lo) + (ch >> 6) * 128 + 64 + (ch & 63)));
+        const uint32_t w[2] = {r.x, r.y};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 t = e4m3x2_to_float2((w[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+            f[2 * j] = fmaf(t.x, 1.0f / LO_SCALE, f[2 * j]);
+            f[2 * j + 1] = fmaf(t.y, 1.0f / LO_SCALE, f[2 * j + 1]);
+        }
+    } else if (lo) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(pix + ch + lo));
         const __half2* hr = reinterpret_cast<const __half2*>(&r);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -33,19 +56,27 @@ __device__ __forceinline__ void load8(const __half* p, int lo, float* f) {
     }
 }
 
-__device__ __forceinline__ void store8(__half* p, int lo, const float* f) {
-    uint32_t hi[4], lw[4];
+__device__ __forceinline__ void store8(__half* pix, int ch, int lo, int fmt, const float* f) {
+    uint32_t hi[4], lw[4], qh[4], ql[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float a0 = fminf(fmaxf(f[2 * j], -65504.0f), 65504.0f), a1 = fminf(fmaxf(f[2 * j + 1], -65504.0f), 65504.0f);
         const __half2 h = __floats2half2_rn(a0, a1);
         hi[j] = *reinterpret_cast<const uint32_t*>(&h);
         const float2 hf = __half22float2(h);
-        const __half2 l = __floats2half2_rn((a0 - hf.x) * LO_SCALE, (a1 - hf.y) * LO_SCALE);
+        const float r0 = (a0 - hf.x) * LO_SCALE, r1 = (a1 - hf.y) * LO_SCALE;
+        const __half2 l = __floats2half2_rn(r0, r1);
         lw[j] = *reinterpret_cast<const uint32_t*>(&l);
+        qh[j] = e4m3x2(a0, a1); ql[j] = e4m3x2(r0, r1);
     }
-    *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    if (lo) *reinterpret_cast<uint4*>(p + lo) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    *reinterpret_cast<uint4*>(pix + ch) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (lo && fmt == 2) {
+        uint8_t* g = reinterpret_cast<uint8_t*>(pix + lo) + (ch >> 6) * 128 + (ch & 63);
+        *reinterpret_cast<uint2*>(g) = make_uint2(qh[0] | (qh[1] << 16), qh[2] | (qh[3] << 16));
+        *reinterpret_cast<uint2*>(g + 64) = make_uint2(ql[0] | (ql[1] << 16), ql[2] | (ql[3] << 16));
+    } else if (lo) {
+        *reinterpret_cast<uint4*>(pix + ch + lo) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ conv_first
@@ -53,7 +84,7 @@ template <int COUT>
 __global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict__ x, int n, int cin, int h, int w,
                                                          const float* __restrict__ wt,      // [9*cin][COUT]
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
-                                                         __half* __restrict__ dst, int dst_ld, int dst_lo, int relu) {
+                                                         __half* __restrict__ dst, int dst_ld, int dst_lo, int relu, int fmt) {
     extern __shared__ float s_w[];                    // 9*cin*COUT weights, then scale, shift
     const int nw = 9 * cin * COUT;
     for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = wt[i];
@@ -97,7 +128,7 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict
                 float4* of = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + pix * dst_ld + 8 * c8);
                 of[0] = make_float4(f[0], f[1], f[2], f[3]); of[1] = make_float4(f[4], f[5], f[6], f[7]);
             } else {
-                store8(o + 8 * c8, dst_lo, f);
+                store8(o, 8 * c8, dst_lo, fmt, f);
             }
         }
     }
@@ -112,13 +143,13 @@ __global__ void __launch_bounds__(256) maxpool2x2_kernel(const __half* __restric
         const int cc = (int)(i % c8); size_t t = i / c8;
         const int xo = (int)(t % wo); t /= wo;
         const int yo = (int)(t % ho); const int img = (int)(t / ho);
-        const __half* p = src + (((size_t)img * h + 2 * yo) * w + 2 * xo) * ld_src + 8 * cc;
+        const __half* p = src + (((size_t)img * h + 2 * yo) * w + 2 * xo) * ld_src;
         float a[8], b[8], d[8], e[8];
-        load8(p, lo_src, a); load8(p + ld_src, lo_src, b);
-        load8(p + (size_t)w * ld_src, lo_src, d); load8(p + (size_t)w * ld_src + ld_src, lo_src, e);
+        load8(p, 8 * cc, lo_src, 1, a); load8(p + ld_src, 8 * cc, lo_src, 1, b);
+        load8(p + (size_t)w * ld_src, 8 * cc, lo_src, 1, d); load8(p + (size_t)w * ld_src + ld_src, 8 * cc, lo_src, 1, e);
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] = fmaxf(fmaxf(a[j], b[j]), fmaxf(d[j], e[j]));
-        store8(dst + (((size_t)img * ho + yo) * wo + xo) * ld_dst + 8 * cc, lo_dst, a);     // hi/lo split of an exact value: lossless
+        store8(dst + (((size_t)img * ho + yo) * wo + xo) * ld_dst, 8 * cc, lo_dst, 1, a);    // re-split of the fp32 sum hi + lo/2048
     }
 }
 
@@ -143,7 +174,7 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __half* __restric
 __global__ void __launch_bounds__(256) att_gate_kernel(const __half* __restrict__ a, int f_int, int ld_a, int lo_a,
                                                        const __half* __restrict__ x, int f_l, int ld_x, int lo_x,
                                                        const float* __restrict__ w_psi, float psi_scale, float psi_shift,
-                                                       __half* __restrict__ dst, int ld_dst, int c_off, int lo_dst, size_t npix, int gs) {
+                                                       __half* __restrict__ dst, int ld_dst, int c_off, int lo_dst, size_t npix, int gs, int fmt) {
     extern __shared__ float s_wp[];
     for (int i = threadIdx.x; i < f_int; i += blockDim.x) s_wp[i] = w_psi[i];
     __syncthreads();
@@ -161,7 +192,7 @@ __global__ void __launch_bounds__(256) att_gate_kernel(const __half* __restrict_
             const __half* ap = a + pix * ld_a;
             for (int ch = gl; ch < f_int / 8; ch += gs) {
                 float f[8];
-                load8(ap + 8 * ch, lo_a, f);
+                load8(ap, 8 * ch, lo_a, fmt, f);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dot = fmaf(f[j], s_wp[8 * ch + j], dot);
             }
@@ -171,13 +202,13 @@ __global__ void __launch_bounds__(256) att_gate_kernel(const __half* __restrict_
         const float psi = 1.0f / (1.0f + expf(-z));
         if (live) {
             const __half* xp = x + pix * ld_x;
-            __half* op = dst + pix * ld_dst + c_off;
+            __half* op = dst + pix * ld_dst;
             for (int ch = gl; ch < f_l / 8; ch += gs) {
                 float f[8];
-                load8(xp + 8 * ch, lo_x, f);
+                load8(xp, 8 * ch, lo_x, fmt, f);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] *= psi;
-                store8(op + 8 * ch, lo_dst, f);
+                store8(op, c_off + 8 * ch, lo_dst, fmt, f);
             }
         }
     }
@@ -188,7 +219,7 @@ template <int COUT>
 __global__ void __launch_bounds__(256) conv1x1_head_kernel(const __half* __restrict__ src, int c_in, int ld_src, int lo_src,
                                                            const float* __restrict__ wt,     // [COUT][c_in]
                                                            const float* __restrict__ bias, int sigmoid,
-                                                           float* __restrict__ dst, float* __restrict__ dst_max, int n, size_t hw) {
+                                                           float* __restrict__ dst, float* __restrict__ dst_max, int n, size_t hw, int fmt) {
     extern __shared__ float s_w[];
     for (int i = threadIdx.x; i < COUT * c_in; i += blockDim.x) s_w[i] = wt[i];
     __syncthreads();
@@ -200,7 +231,7 @@ __global__ void __launch_bounds__(256) conv1x1_head_kernel(const __half* __restr
         const __half* sp = src + pix * ld_src;
         for (int ch = 0; ch < c_in / 8; ++ch) {
             float f[8];
-            load8(sp + 8 * ch, lo_src, f);
+            load8(sp, 8 * ch, lo_src, fmt, f);
 #pragma unroll
             for (int c = 0; c < COUT; ++c) {
                 const float* wr = s_w + c * c_in + 8 * ch;
@@ -237,8 +268,14 @@ static int check_plane(const char* who, int c, int ld, int lo) {
     return NBP_OK;
 }
 
+static int check_fmt(const char* who, int fmt, int lo) {
+    if (fmt != 1 && fmt != 2) return invalid("%s: fmt must be 1 (fp16 lo plane) or 2 (e4m3 pair plane), got %d", who, fmt);
+    if (fmt == 2 && (lo <= 0 || lo % 64)) return invalid("%s: the e4m3 pair plane needs a 64-channel aligned second-plane offset (lo=%d)", who, lo);
+    return NBP_OK;
+}
+
 extern "C" int nbp_conv_first(const float* x, int n, int c_in, int h, int w, const float* weight, const float* scale,
-                              const float* shift, int c_out, int relu, void* dst, int dst_ld, int dst_lo, void* stream) {
+                              const float* shift, int c_out, int relu, void* dst, int dst_ld, int dst_lo, int fmt, void* stream) {
     if (!x || !weight || !scale || !shift || !dst) return invalid("nbp_conv_first: null pointer argument");
     if (n <= 0 || h <= 0 || w <= 0 || c_in <= 0 || c_in > 16) return invalid("nbp_conv_first: bad sizes n=%d c_in=%d h=%d w=%d", n, c_in, h, w);
     if (c_out != 64) return invalid("nbp_conv_first: c_out must be 64 (got %d)", c_out);
@@ -246,9 +283,10 @@ extern "C" int nbp_conv_first(const float* x, int n, int c_in, int h, int w, con
                         : check_plane("nbp_conv_first", c_out, dst_ld, dst_lo);
     if (rc) return rc;
     if ((uintptr_t)dst & 15) return invalid("nbp_conv_first: dst must be 16-byte aligned");
+    if (dst_lo >= 0 && (rc = check_fmt("nbp_conv_first", fmt, fmt == 2 ? dst_lo : 64))) return rc;
     const size_t smem = sizeof(float) * (size_t)(9 * c_in * 64 + 128);
     conv_first_kernel<64><<<grid_for((size_t)n * h * w, 128), 128, smem, (cudaStream_t)stream>>>(x, n, c_in, h, w, weight, scale, shift,
-                                                                                                  (__half*)dst, dst_ld, dst_lo, relu);
+                                                                                                  (__half*)dst, dst_ld, dst_lo, relu, fmt);
     count_launch();
     return check_cuda(cudaGetLastError(), "nbp_conv_first launch");
 }
@@ -286,8 +324,9 @@ extern "C" int nbp_upsample2x(const void* src, int n, int h, int w, int c, int l
 
 extern "C" int nbp_att_gate(const void* a, int f_int, int ld_a, int lo_a, const void* x, int f_l, int ld_x, int lo_x,
                             const float* w_psi, float psi_scale, float psi_shift,
-                            void* dst, int dst_ld, int dst_c_off, int dst_lo, int64_t npix, void* stream) {
+                            void* dst, int dst_ld, int dst_c_off, int dst_lo, int64_t npix, int fmt, void* stream) {
     if (!a || !x || !w_psi || !dst) return invalid("nbp_att_gate: null pointer argument");
+    if (int rf = check_fmt("nbp_att_gate", fmt, fmt == 2 ? (lo_a | lo_x | dst_lo | (dst_c_off % 64 ? 1 : 0)) : 64)) return rf;
     if (f_int <= 0 || f_int % 8 || f_l <= 0 || f_l % 8 || npix <= 0) return invalid("nbp_att_gate: bad sizes f_int=%d f_l=%d npix=%lld", f_int, f_l, (long long)npix);
     int rc = check_plane("nbp_att_gate(a)", f_int, ld_a, lo_a);
     if (rc) return rc;
@@ -300,14 +339,15 @@ extern "C" int nbp_att_gate(const void* a, int f_int, int ld_a, int lo_a, const 
     const size_t warps = ((size_t)npix + (32 / gs) - 1) / (32 / gs);
     att_gate_kernel<<<grid_for(warps * 32, 256, 2), 256, sizeof(float) * f_int, (cudaStream_t)stream>>>(
         (const __half*)a, f_int, ld_a, lo_a, (const __half*)x, f_l, ld_x, lo_x, w_psi, psi_scale, psi_shift,
-        (__half*)dst, dst_ld, dst_c_off, dst_lo, (size_t)npix, gs);
+        (__half*)dst, dst_ld, dst_c_off, dst_lo, (size_t)npix, gs, fmt);
     count_launch();
     return check_cuda(cudaGetLastError(), "nbp_att_gate launch");
 }
 
 extern "C" int nbp_conv1x1_head(const void* src, int c_in, int ld_src, int lo_src, const float* weight, const float* bias, int c_out,
-                                int sigmoid, float* dst, float* dst_max, int n, int64_t hw, void* stream) {
+                                int sigmoid, float* dst, float* dst_max, int n, int64_t hw, int fmt, void* stream) {
     if (!src || !weight || !bias || !dst) return invalid("nbp_conv1x1_head: null pointer argument");
+    if (int rf = check_fmt("nbp_conv1x1_head", fmt, fmt == 2 ? lo_src : 64)) return rf;
     if (c_in <= 0 || c_in % 8 || n <= 0 || hw <= 0) return invalid("nbp_conv1x1_head: bad sizes");
     int rc = check_plane("nbp_conv1x1_head", c_in, ld_src, lo_src);
     if (rc) return rc;
@@ -315,8 +355,8 @@ extern "C" int nbp_conv1x1_head(const void* src, int c_in, int ld_src, int lo_sr
     const size_t smem = sizeof(float) * (size_t)c_out * c_in;
     const int g = grid_for((size_t)n * hw, 256);
     cudaStream_t st = (cudaStream_t)stream;
-    if (c_out == 8) conv1x1_head_kernel<8><<<g, 256, smem, st>>>((const __half*)src, c_in, ld_src, lo_src, weight, bias, sigmoid, dst, dst_max, n, (size_t)hw);
-    else if (c_out == 1) conv1x1_head_kernel<1><<<g, 256, smem, st>>>((const __half*)src, c_in, ld_src, lo_src, weight, bias, sigmoid, dst, dst_max, n, (size_t)hw);
+    if (c_out == 8) conv1x1_head_kernel<8><<<g, 256, smem, st>>>((const __half*)src, c_in, ld_src, lo_src, weight, bias, sigmoid, dst, dst_max, n, (size_t)hw, fmt);
+    else if (c_out == 1) conv1x1_head_kernel<1><<<g, 256, smem, st>>>((const __half*)src, c_in, ld_src, lo_src, weight, bias, sigmoid, dst, dst_max, n, (size_t)hw, fmt);
     else return invalid("nbp_conv1x1_head: c_out must be 1 or 8 (got %d)", c_out);
     count_launch();
     return check_cuda(cudaGetLastError(), "nbp_conv1x1_head launch");

