@@ -193,6 +193,7 @@ int nbp_conv_first(const float* x, int n, int c_in, int h, int w, const float* w
 int nbp_maxpool2x2(const void* src, int n, int h, int w, int c, int ld_src, int lo_src, void* dst, int ld_dst, int lo_dst, void* stream);
 int nbp_upsample2x(const void* src, int n, int h, int w, int c, int ld_src, int lo_src, void* dst, int ld_dst, int lo_dst, void* stream);
 /* Attention_block tail (nbp_model.py:49-62): psi = sigmoid(psi_scale * dot(a, w_psi) + psi_shift); dst = x * psi.
+ * `fmt` applies to x and dst; `a` (never a GEMM operand, f_int may be 32) always carries the fp16 lo plane (format 1).
  * a [npix] x f_int = relu(BN(W_g g) + BN(W_x x)); x [npix] x f_l; dst written at channel dst_c_off */
 int nbp_att_gate(const void* a, int f_int, int ld_a, int lo_a, const void* x, int f_l, int ld_x, int lo_x,
                  const float* w_psi, float psi_scale, float psi_shift,
@@ -202,6 +203,18 @@ int nbp_att_gate(const void* a, int f_int, int ld_a, int lo_a, const void* x, in
  * heading read-out `torch.max(predicted_value_map, dim=1)` of next_best_path/testers/nbp_planning.py:193 fused into the head */
 int nbp_conv1x1_head(const void* src, int c_in, int ld_src, int lo_src, const float* weight, const float* bias, int c_out,
                      int sigmoid, float* dst, float* dst_max, int n, int64_t hw, int fmt, void* stream);
+
+/* ------------------------------------------------------------------------------------------ section 8f row 3 (second half)
+ * Ground-truth obstacle map of the data collection: get_binary_obstacle_array(mesh, camera_pose, view_size)
+ * (next_best_path/utility/utils.py:226-262, called at nbp_utils.py:638 -> `current_gt_2d_layout`): the mesh cut by the horizontal
+ * plane through the camera (trimesh.intersections.mesh_plane), drawn as lines into a view_size x view_size window centred on the
+ * camera and binarised at S x S (rows towards -z, columns towards -x).  One call for n_maps (scene, pose) pairs.
+ * meshes: packed as for nbp_raster_depth_batched; map_scene[n_maps] (NULL = identity) = scene of map b; pose [n_maps][5];
+ * out [n_maps][S][S] fp32 of 0/1 (zeroed by the call); half_width_px = half the drawn line width in output pixels
+ * (1.35 = matplotlib's default 1.5 pt line after the reference's resize).  Geometry restated in oracle/section_oracle.c. */
+int nbp_gt_obstacle_map(const float* verts, const int32_t* faces, const int64_t* vert_offsets, const int64_t* face_offsets,
+                        const int32_t* map_scene, const float* pose, int n_maps, int64_t max_faces_per_scene, int S,
+                        float view_size, float half_width_px, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------ a11 (train mode), a13
  * Train-mode BatchNorm2d (batch statistics, running-stat update: momentum 0.1, unbiased running variance, eps 1e-5 --

@@ -77,6 +77,7 @@ SIGNATURES.update({
     "nbp_debug_attach_wgrad": (_i, [_p]),
     "nbp_obstacle_fuse": (_i, [_p, _p, _l, _p, _l, _p, _l, _i, _i, _f, _p, _p, _p]),
     "nbp_candidate_scores": (_i, [_p, _p, _i, _p, _p, _p, _i, _i, _p, _i, _i, _f, _f, _i, _p, _p, _p, _p, _p]),
+    "nbp_gt_obstacle_map": (_i, [_p, _p, _p, _p, _p, _p, _i, _l, _i, _f, _f, _p, _p]),
     "nbp_segments_hit_mesh": (_i, [_p, _p, _p, _p, _i, _p, _p, _i, _i, _p, _p, _p]),
     "nbp_coverage_percentage": (_i, [_p, _l, _p, _p, _l, _p, _p, _p, _p, _p, _p, _i, _l, _l, _f, _f, _i, C.c_uint64, _p, _p, _p, _p]),
 })

@@ -15,6 +15,9 @@ import torch
 from . import _lib
 
 
+GT_MAP_HALF_WIDTH_PX = 1.35      # matplotlib's default 1.5 pt line at dpi 100 after the reference's resize to 256 px (oracle/section_oracle.c)
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -31,6 +34,7 @@ class MeshBatch:
         self.vert_off = torch.tensor(np.concatenate([[0], np.cumsum([len(v) for v in vs])]), dtype=torch.int64, device=self.dev)
         self.face_off = torch.tensor(np.concatenate([[0], np.cumsum([len(f) for f in fs])]), dtype=torch.int64, device=self.dev)
         self.n_scenes = len(vs)
+        self.max_faces = max([len(f) for f in fs] + [0])
 
     def _run(self, seg, seg_scene, rays, want_count):
         seg = torch.as_tensor(seg, dtype=torch.float32).reshape(-1, 6).contiguous().to(self.dev)
@@ -58,6 +62,26 @@ class MeshBatch:
         seg = torch.cat((torch.as_tensor(origins, dtype=torch.float32).reshape(-1, 3), torch.as_tensor(directions, dtype=torch.float32).reshape(-1, 3)), dim=1)
         return self._run(seg, ray_scene, True, True)[1]
 
+    def gt_obstacle_maps(self, poses, map_scene=None, S: int = 256, view_size: float = 80.0, half_width_px: float = GT_MAP_HALF_WIDTH_PX):
+        """Ground-truth obstacle maps: poses (n,5) camera poses, map_scene (n,) scene of each map (default:
+        map b <- scene b).  Returns (n,1,S,S) fp32 of 0/1 on the device = ``current_gt_obs`` of nbp_utils.py:638-639, all maps in one
+        launch (the reference: trimesh section + matplotlib + PIL per pose on the host)."""
+        pose = torch.as_tensor(poses, dtype=torch.float32).reshape(-1, 5).contiguous().to(self.dev)
+        n = pose.shape[0]
+        if map_scene is None:
+            if n != self.n_scenes:
+                raise RuntimeError("gt_obstacle_maps: pass map_scene when the number of poses differs from the number of scenes")
+            ms = None
+        else:
+            ms = torch.as_tensor(map_scene).to(device=self.dev, dtype=torch.int32).contiguous()
+            assert ms.numel() == n
+        out = torch.empty((n, 1, S, S), dtype=torch.float32, device=self.dev)
+        rc = _lib.lib().nbp_gt_obstacle_map(self.verts.data_ptr(), self.faces.data_ptr(), self.vert_off.data_ptr(), self.face_off.data_ptr(),
+                                            ms.data_ptr() if ms is not None else None, pose.data_ptr(), n, self.max_faces, S,
+                                            float(view_size), float(half_width_px), out.data_ptr(), _stream())
+        _lib.check(rc, "nbp_gt_obstacle_map")
+        return out
+
     def neighbour_collision_table(self, positions, neighbours, scene: int = 0):
         """positions (P,3), neighbours (P,K) indices into positions (-1 = none): blocked (P,K) bool = the move crosses the mesh.
         One launch instead of P*K host ray casts inside Dijkstra (long_term_utils.py:334-359)."""
@@ -83,3 +107,10 @@ def check_camera_in_mesh(mesh_for_check: MeshBatch, camera_position):
     d = torch.tensor([[0.0, 1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
     c = mesh_for_check.ray_hit_counts(o, d).cpu()
     return bool((c % 2 == 1).all())
+
+
+def get_binary_obstacle_array(mesh: MeshBatch, camera_pose, view_size=80):
+    """Drop-in for next_best_path/utility/utils.py:226-262 with ``mesh`` a one-scene MeshBatch: (256, 256) int numpy array of 0/1
+    (the reference returns None when the plane misses the mesh; here the map is then all zeros)."""
+    m = mesh.gt_obstacle_maps(torch.as_tensor(camera_pose, dtype=torch.float32).reshape(1, 5), map_scene=[0], view_size=float(view_size))
+    return m[0, 0].cpu().numpy().astype(int)

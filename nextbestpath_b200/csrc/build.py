@@ -19,6 +19,7 @@ SOURCES = {
     "planner.cu": ["-fmad=false"],
     "coverage.cu": ["-fmad=false"],
     "collision.cu": ["-fmad=false"],
+    "section.cu": ["-fmad=false"],
     "conv_tc.cu": [],
     "nn_kernels.cu": [],
     "train_kernels.cu": [],

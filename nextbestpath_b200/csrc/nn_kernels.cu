@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) att_gate_kernel(const __half* __restrict_
             const __half* ap = a + pix * ld_a;
             for (int ch = gl; ch < f_int / 8; ch += gs) {
                 float f[8];
-                load8(ap, 8 * ch, lo_a, fmt, f);
+                load8(ap, 8 * ch, lo_a, 1, f);                    // `a` is never a GEMM operand: always the fp16 lo plane
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dot = fmaf(f[j], s_wp[8 * ch + j], dot);
             }
@@ -326,7 +326,7 @@ extern "C" int nbp_att_gate(const void* a, int f_int, int ld_a, int lo_a, const 
                             const float* w_psi, float psi_scale, float psi_shift,
                             void* dst, int dst_ld, int dst_c_off, int dst_lo, int64_t npix, int fmt, void* stream) {
     if (!a || !x || !w_psi || !dst) return invalid("nbp_att_gate: null pointer argument");
-    if (int rf = check_fmt("nbp_att_gate", fmt, fmt == 2 ? (lo_a | lo_x | dst_lo | (dst_c_off % 64 ? 1 : 0)) : 64)) return rf;
+    if (int rf = check_fmt("nbp_att_gate", fmt, fmt == 2 ? (lo_x | dst_lo | (dst_c_off % 64 ? 1 : 0)) : 64)) return rf;
     if (f_int <= 0 || f_int % 8 || f_l <= 0 || f_l % 8 || npix <= 0) return invalid("nbp_att_gate: bad sizes f_int=%d f_l=%d npix=%lld", f_int, f_l, (long long)npix);
     int rc = check_plane("nbp_att_gate(a)", f_int, ld_a, lo_a);
     if (rc) return rc;

@@ -409,7 +409,7 @@ def _forward_eval(pk, x, out1, out2, vmax):
         g = cat.channels(f_l, f_l)
         _conv(pk, pk[f"Up{t}"], B, d, 4, g, up2x=True)   # upsample fused: d is read at its own (half) resolution
         att = pk[f"Att{t}"]
-        arelu = new(skip.h, skip.w, att["c_out"], fmt)
+        arelu = new(skip.h, skip.w, att["c_out"], 1)     # read by the gate kernel only (f_int can be 32 < one e4m3 group): 22-bit format
         _conv(pk, att, B, g, 1, arelu, relu=True, src1=skip)
         gated = cat.channels(0, f_l)
         _lib.check(L.nbp_att_gate(arelu.ptr, arelu.c, arelu.ld, arelu.lo, skip.ptr, f_l, skip.ld, skip.lo,

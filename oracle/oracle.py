@@ -41,8 +41,8 @@ f32 = np.float32
 def build(verbose: bool = False) -> str:
     """Compile oracle/raster_oracle.c -> oracle/_build/liboracle.so (idempotent)."""
     out = os.path.join(_HERE, "_build", "liboracle.so")
-    src = os.path.join(_HERE, "raster_oracle.c")
-    if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("raster_oracle.c", "section_oracle.c")]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in srcs):
         r = subprocess.run(["make", "-C", _HERE], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
@@ -62,6 +62,8 @@ def _lib():
         lib.nbp_oracle_render_depth.argtypes = [fp, ctypes.c_int64, lp, ctypes.c_int64, fp, fp,
                                                 ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                                 fp, ip, ctypes.c_int]
+        lib.nbp_oracle_plane_section_map.restype = ctypes.c_int
+        lib.nbp_oracle_plane_section_map.argtypes = [fp, lp, ctypes.c_int64, fp, ctypes.c_int, ctypes.c_float, ctypes.c_float, fp, fp]
         _LIB = lib
     return _LIB
 
@@ -414,3 +416,22 @@ def segment_mesh_hits(verts, faces, segments, rays: bool = False):
                 ok &= np.sqrt(_dot3(dl, dl)) < length
         count[i] = int(ok.sum()); hit[i] = bool(ok.any())
     return hit, count
+
+
+# --------------------------------------------------------------------------- f3 ground-truth obstacle map
+GT_MAP_HALF_WIDTH_PX = 1.35      # matplotlib's 1.5 pt line at 100 dpi, after the resize of the ~198 px axes to 256 px (section_oracle.c)
+
+
+def gt_obstacle_map(verts, faces, pose, S: int = 256, view: float = 80.0, half_width: float = GT_MAP_HALF_WIDTH_PX, return_segments=False):
+    """get_binary_obstacle_array(mesh, camera_pose, view_size) next_best_path/utility/utils.py:226-262 (called nbp_utils.py:638):
+    the mesh cut by the horizontal plane through the camera, drawn into an S x S binary image centred on the camera
+    (rows towards -z, columns towards -x).  Restatement in oracle/section_oracle.c -- PARITY UNPINNED (trimesh / matplotlib absent).
+    Returns (S, S) float32 of 0/1 [, (n_seg, 4) segments x0, z0, x1, z1]."""
+    v = np.ascontiguousarray(verts, dtype=f32)
+    f = np.ascontiguousarray(faces, dtype=np.int64)
+    p = np.ascontiguousarray(np.asarray(pose, dtype=f32).reshape(-1)[:3])
+    out = np.zeros((S, S), dtype=f32)
+    seg = np.zeros((max(len(f), 1), 4), dtype=f32)
+    n = _lib().nbp_oracle_plane_section_map(_fp(v), f.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), f.shape[0], _fp(p), int(S),
+                                            float(view), float(half_width), _fp(out), _fp(seg))
+    return (out, seg[:n].copy()) if return_segments else out

@@ -340,7 +340,7 @@ def test_conv_fwd_e4m3_correction_mode(n, h, w, c0, c1, cout, taps, up):
     a1 = M._Act(*_to_act_fmt2(x[:, c0:]), h, w, 0, 2) if c1 else None
     oh, ow = (2 * h, 2 * w) if up else (h, w)
     outs = {}
-    for fmt in (2, 1):
+    for fmt in ((2, 1) if cout % 64 == 0 else (1,)):
         y = M._Act(torch.zeros((n, oh, ow, 2 * cout), dtype=torch.float16, device=DEV), cout, 2 * cout, cout, oh, ow, 0, fmt)
         M._conv({"precise": True}, layer, n, a0, taps, y, relu=False, src1=a1, up2x=bool(up))
         torch.cuda.synchronize()
@@ -372,9 +372,12 @@ def test_conv_fwd_e4m3_correction_mode(n, h, w, c0, c1, cout, taps, up):
     want = conv_q(xh, q_hi16) + (conv_q(x8, q_lo8) + conv_q(xl8, q_w8)) / (2048.0 * sw)
     want = (want * scale.double()[None, :, None, None] + shift.double()[None, :, None, None]).permute(0, 2, 3, 1)
     exact = (conv(xd, wt.double()) * scale.double()[None, :, None, None] + shift.double()[None, :, None, None]).permute(0, 2, 3, 1)
-    v2, q2 = _from_act_fmt2(outs[2], cout)
-    v1 = _from_act(outs[1], cout, cout)
     rel = lambda a_, b_: float((a_.double() - b_).norm() / b_.norm())
+    v1 = _from_act(outs[1], cout, cout)
+    if 2 not in outs:                                              # 32-channel outputs exist in the fp16 lo-plane format only
+        assert rel(v1, want) <= 2e-6 and rel(v1, exact) <= 1e-4
+        return
+    v2, q2 = _from_act_fmt2(outs[2], cout)
     print(f"n={n} h={h} w={w} c={c0}+{c1} cout={cout} taps={taps} up={up}: vs same arithmetic in fp64 {rel(v1, want):.2e}; "
           f"vs unquantised conv {rel(v1, exact):.2e}; e4m3-pair output {rel(v2, want):.2e}")
     assert rel(v1, want) <= 2e-6                                   # the kernel computes what the format defines
