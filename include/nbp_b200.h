@@ -136,8 +136,8 @@ typedef struct nbp_conv_desc {
     int precise;                           /* numeric mode = format of the SOURCE tensors and of the weights:
                                               0: single fp16 plane;
                                               1: fp16x2 split format (hi plane + lo*2048 plane), 3 tensor passes, fp32-grade results;
-                                              2: fp16 hi plane + an e4m3 pair plane (per 64-channel group: 64 bytes e4m3(x), then 64 bytes
-                                                 e4m3((x - hi) * 2048)); the hi product runs on the fp16 pipe, both correction products as one
+                                              2: fp16 hi plane + an e4m3 pair plane (per 64-channel group: 64 bytes e4m3(x / 8), then 64 bytes
+                                                 e4m3((x - hi) * 2048 / 8)); the hi product runs on the fp16 pipe, both correction products as one
                                                  e4m3 reduction (kind::f8f6f4, 2x rate): 2 pass-equivalents, ~15-bit operands */
     const void* src0; int c0; int ld0; int lo0;  /* NHWC fp16: c0 channels per pixel, pixel stride ld0 elements; with
                                               precise, the lo plane starts lo0 elements after src0 */
@@ -167,6 +167,10 @@ typedef struct nbp_conv_desc {
                                               A mode-1 layer may write format 2 and vice versa: the network mixes both (nbp_model.py) */
     int pool_fmt;                          /* same for pool_dst */
     float w_lo_scale;                      /* mode 2: 1 / (2048 s), s = the power of two the e4m3 weight rows were scaled by */
+    uint64_t* sat_count;                   /* optional device counter (NULL = off): += 1 for every (pixel, 32-channel group) written in
+                                              format 2 in which a value exceeded the e4m3 window (|x| > 3584: the planes hold x / 8).  Such
+                                              elements fall back to fp16 precision; a non-zero count means the inputs are far outside the
+                                              range the BatchNorm statistics were calibrated for */
     void* pool_dst; int pool_ld; int pool_lo_off; /* optional (NULL = off): ALSO write nn.MaxPool2d(2,2) of the output (nbp_model.py:68,113-121)
                                               as an NHWC fp16 tensor [n][h/2][w/2][pool_ld] (lo plane pool_lo_off elements after the hi
                                               channels), fused into the epilogue: the encoder needs both the skip tensor and its pooled

@@ -42,7 +42,7 @@ class ConvDesc(C.Structure):
                 ("n", _i), ("h", _i), ("w", _i), ("taps", _i), ("up2x", _i), ("weight", _p), ("c_out", _i),
                 ("scale", _p), ("shift", _p), ("relu", _i), ("dst", _p), ("dst_ld", _i), ("dst_c_off", _i),
                 ("dst_lo_off", _i), ("out_f32", _i), ("k_chunk", _i), ("dst_fmt", _i), ("pool_fmt", _i), ("w_lo_scale", _f),
-                ("pool_dst", _p), ("pool_ld", _i), ("pool_lo_off", _i)]
+                ("sat_count", _p), ("pool_dst", _p), ("pool_ld", _i), ("pool_lo_off", _i)]
 
 
 SIGNATURES.update({

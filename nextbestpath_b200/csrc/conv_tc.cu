@@ -72,6 +72,7 @@ struct ConvKParams {
     int lo0, lo1;                       // element offset of the lo plane inside the tensor maps (PRECISE)
     float lo_scale;                     // acc = acc_hi + acc_lo * lo_scale (1/2048 for fp16x2, 1/(2048 s) for fp16+e4m3)
     int dst_fmt, pool_fmt;              // second-plane format written by the epilogue: 1 = fp16 lo*2048, 2 = e4m3 pair (MODE 2 consumers)
+    unsigned long long* sat_count;      // optional: += number of (pixel, 32-channel group) stores in which an e4m3 value saturated
     int out_f32;                        // 1: the destination is plain fp32 NHWC (gradients), no fp16 planes
     int kchunk;                         // K stages accumulated inside TMEM before the partial sum is folded into fp32
                                         // registers (round-to-nearest); the tensor core's own accumulator truncates
@@ -327,6 +328,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                 auto split_store = [&](__half* pix, int ch, int lo_off, int fmt, const float* x) {
                     uint32_t packed[16], packed_lo[16];
                     uint32_t p8h[8], p8l[8];
+                    bool sat = false;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const __half2 h = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
@@ -336,7 +338,9 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                             const float r0 = (x[2 * j] - hf.x) * 2048.0f, r1 = (x[2 * j + 1] - hf.y) * 2048.0f;
                             const __half2 l = __floats2half2_rn(r0, r1);
                             packed_lo[j] = *reinterpret_cast<const uint32_t*>(&l);
-                            const uint32_t qh = e4m3x2(x[2 * j], x[2 * j + 1]), ql = e4m3x2(r0, r1);
+                            const uint32_t qh = e4m3x2(x[2 * j] * NBP_E4M3_ACT_SCALE, x[2 * j + 1] * NBP_E4M3_ACT_SCALE);
+                            const uint32_t ql = e4m3x2(r0 * NBP_E4M3_ACT_SCALE, r1 * NBP_E4M3_ACT_SCALE);
+                            sat |= fmaxf(fabsf(x[2 * j]), fabsf(x[2 * j + 1])) > NBP_E4M3_MAX / NBP_E4M3_ACT_SCALE;
                             if (j & 1) { p8h[j >> 1] |= qh << 16; p8l[j >> 1] |= ql << 16; } else { p8h[j >> 1] = qh; p8l[j >> 1] = ql; }
                         }
                     }
@@ -349,6 +353,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                             uint4* oh = reinterpret_cast<uint4*>(g); uint4* ol = reinterpret_cast<uint4*>(g + 64);
                             oh[0] = make_uint4(p8h[0], p8h[1], p8h[2], p8h[3]); oh[1] = make_uint4(p8h[4], p8h[5], p8h[6], p8h[7]);
                             ol[0] = make_uint4(p8l[0], p8l[1], p8l[2], p8l[3]); ol[1] = make_uint4(p8l[4], p8l[5], p8l[6], p8l[7]);
+                            if (sat && p.sat_count) atomicAdd(p.sat_count, 1ull);          // rare by construction: out-of-range inputs only
                         } else {
                             uint4* ol = reinterpret_cast<uint4*>(pix + ch + lo_off);
 #pragma unroll
@@ -567,7 +572,8 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     kp.m_tiles = kp.tiles_x * kp.tiles_y * kp.tiles_n; kp.n_tiles = d->c_out / block_n;
     kp.taps = d->taps; kp.kc0 = d->c0 / BLOCK_K; kp.kc1 = d->c1 / BLOCK_K;
     kp.lo0 = d->lo0; kp.lo1 = d->lo1;
-    kp.lo_scale = fp8 ? d->w_lo_scale : 1.0f / 2048.0f;
+    kp.lo_scale = fp8 ? d->w_lo_scale / NBP_E4M3_ACT_SCALE : 1.0f / 2048.0f;
+    kp.sat_count = (unsigned long long*)d->sat_count;
     kp.dst_fmt = dst_fmt; kp.pool_fmt = pool_fmt;
     kp.up2x = d->up2x ? 1 : 0;
     kp.out_f32 = d->out_f32 ? 1 : 0;

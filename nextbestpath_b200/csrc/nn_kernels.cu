@@ -15,8 +15,8 @@ namespace nbp {
 // Activation format helpers.  A tensor is NHWC fp16; `pix` points at the first element of a pixel, `ch` is a channel index
 // (multiple of 8) and `lo` the offset of the pixel's second plane (0: single fp16 plane).  Second-plane formats (`fmt`):
 //   1  fp16x2: fp16 (value - hi) * 2048 at the same channel index
-//   2  e4m3 pair: per 64-channel group 64 bytes e4m3(value) followed by 64 bytes e4m3((value - hi) * 2048) -- the operand layout of
-//      the conv kernel's fp16 + e4m3 mode; the value read back is hi + e4m3_lo / 2048 (~15 bits)
+//   2  e4m3 pair: per 64-channel group 64 bytes e4m3(value / 8) followed by 64 bytes e4m3((value - hi) * 2048 / 8) -- the operand layout
+//      of the conv kernel's fp16 + e4m3 mode (NBP_E4M3_ACT_SCALE); the value read back is hi + 8 * e4m3_lo / 2048 (~15 bits)
 static constexpr float LO_SCALE = 2048.0f;
 
 __device__ __forceinline__ uint32_t e4m3x2(float a, float b) {           // low byte = a; round to nearest even, saturating
@@ -41,8 +41,8 @@ __device__ __forceinline__ void load8(const __half* pix, int ch, int lo, int fmt
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float2 t = e4m3x2_to_float2((w[j >> 1] >> (16 * (j & 1))) & 0xffffu);
-            f[2 * j] = fmaf(t.x, 1.0f / LO_SCALE, f[2 * j]);
-            f[2 * j + 1] = fmaf(t.y, 1.0f / LO_SCALE, f[2 * j + 1]);
+            f[2 * j] = fmaf(t.x, 1.0f / (LO_SCALE * NBP_E4M3_ACT_SCALE), f[2 * j]);
+            f[2 * j + 1] = fmaf(t.y, 1.0f / (LO_SCALE * NBP_E4M3_ACT_SCALE), f[2 * j + 1]);
         }
     } else if (lo) {
         const uint4 r = __ldg(reinterpret_cast<const uint4*>(pix + ch + lo));
@@ -67,7 +67,7 @@ __device__ __forceinline__ void store8(__half* pix, int ch, int lo, int fmt, con
         const float r0 = (a0 - hf.x) * LO_SCALE, r1 = (a1 - hf.y) * LO_SCALE;
         const __half2 l = __floats2half2_rn(r0, r1);
         lw[j] = *reinterpret_cast<const uint32_t*>(&l);
-        qh[j] = e4m3x2(a0, a1); ql[j] = e4m3x2(r0, r1);
+        qh[j] = e4m3x2(a0 * NBP_E4M3_ACT_SCALE, a1 * NBP_E4M3_ACT_SCALE); ql[j] = e4m3x2(r0 * NBP_E4M3_ACT_SCALE, r1 * NBP_E4M3_ACT_SCALE);
     }
     *reinterpret_cast<uint4*>(pix + ch) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     if (lo && fmt == 2) {

@@ -133,6 +133,12 @@ class NBP(nn.Module):
             b1 = min(x.shape[0], b0 + self.max_chunk)
             _forward_eval(pk, x[b0:b1], out1[b0:b1], out2[b0:b1], vmax[b0:b1])
 
+    def e4m3_saturation_count(self) -> int:
+        """Number of (pixel, 32-channel group) stores, since the weights were last packed, in which an activation left the e4m3
+        window of the "mixed" mode (|x| > 3584) and fell back to fp16 precision.  0 in the calibrated operating range."""
+        pk = self._packed[1] if self._packed is not None else None
+        return int(pk["sat_count"].item()) if pk is not None and "sat_count" in pk else 0
+
     def loss(self, pred1, target1, pred2, target2):
         """nbp_model.py:162-173: MSE/(2 s1^2) + log s1 + BCE/s2^2 + log s2 with s = exp(log_vars)."""
         s1, s2 = torch.exp(2 * self.log_vars[0]), torch.exp(2 * self.log_vars[1])
@@ -207,6 +213,9 @@ def pack_state_dict(sd, precise=True, e4m3_layers=None):
     """Folded / packed parameters for the eval pipeline, from a float32 state_dict on the target device.
     ``e4m3_layers``: predicate(layer name) -> True for the GEMM layers that run nbp_conv_desc mode 2 (fp16 + e4m3 corrections)."""
     pk = {"precise": bool(precise)}
+    if e4m3_layers is not None:
+        # device counter of e4m3 saturation events (nbp_conv_desc.sat_count): stays 0 unless inputs leave the calibrated range
+        pk["sat_count"] = torch.zeros(1, dtype=torch.int64, device=sd["Final1.weight"].device)
 
     def gemm_entry(name, blocks, s_aff, b_aff, c_out, extra=None):
         """blocks: list of (Cout, K) fp32 weight matrices packed one after the other (1, or 4 parity blocks of an up-conv)."""
@@ -310,7 +319,7 @@ def _conv(pk, layer, B, src0, taps, dst, relu=True, src1=None, up2x=False, k_chu
                       layer["scale"].data_ptr(), layer["shift"].data_ptr(), 1 if relu else 0,
                       dst.t.data_ptr(), dst.ld, dst.off, dst.lo, 0, k_chunk,
                       dst.fmt if mode else 0, (pool.fmt if pool is not None else 0) if mode else 0, layer.get("lo_scale", 1.0 / LO_SCALE),
-                      pool.ptr if pool is not None else None, pool.ld if pool is not None else 0, pool.lo if pool is not None else 0)
+                      pk["sat_count"].data_ptr() if "sat_count" in pk else None, pool.ptr if pool is not None else None, pool.ld if pool is not None else 0, pool.lo if pool is not None else 0)
     _lib.check(_lib.lib().nbp_conv_fwd(ctypes.byref(d), _stream()), "nbp_conv_fwd")
 
 

@@ -94,10 +94,8 @@ class RolloutEngine:
     def __init__(self, scenes, nbp, device, S=256, H=256, W=456, max_steps=100, gathering_factor=0.05,
                  sensor_range=70.0, grid_range=(-40.0, 40.0), n_pieces=4, seed=9):
         self.dev = torch.device(device)
-        self.nbp = nbp
-        # the engine consumes (or copies out) the maps of a step before it runs the next forward: let NBP.forward hand out the
-        # output buffers of its captured graph instead of clones.  StepOutput tensors are therefore valid until the next step().
-        nbp.static_outputs = True
+        self.nbp = None
+        self.set_network(nbp)
         self.B, self.S, self.H, self.W = len(scenes), S, H, W
         self.gf, self.sensor_range, self.grid_range, self.n_pieces, self.seed = gathering_factor, sensor_range, grid_range, n_pieces, seed
         dev = self.dev
@@ -140,6 +138,13 @@ class RolloutEngine:
         self._uid_base = torch.arange(B, dtype=torch.int32, device=dev) * 8
         self._copy_stream = None        # side stream of the device->host read-back (created on first use)
         self._copy_done = None
+
+    def set_network(self, nbp):
+        """The engine consumes (or copies out) the maps of a step before it runs the next forward: NBP.forward may hand out the
+        output buffers of its captured graph instead of clones.  StepOutput tensors are therefore valid until the next step()."""
+        self.nbp = nbp
+        if nbp is not None:
+            nbp.static_outputs = True
 
     # ------------------------------------------------------------------ helpers
     def _uids(self, n_slots, slot0):
@@ -194,6 +199,13 @@ class RolloutEngine:
         device; no host synchronisation."""
         return index.coverage(self.cloud, self.cloud_len, weight=weight, seed=self.seed + self.step_idx if seed is None else seed,
                               max_points=self.max_points_bound)
+
+    def build_model_input(self):
+        """Stage B alone: the (B,5,S,S) model input of the current state (used to calibrate / inspect; ``step`` does this itself)."""
+        ops.grid_scatter(self.cloud, self.cloud_len, self.pose, self.slab_bounds, self.n_bounds, self.S, traj=self.traj,
+                         traj_len=self.traj_len, n_pieces=self.n_pieces, grid_range=self.grid_range,
+                         max_points=self.max_points_bound, out=self.grid)
+        return self.grid
 
     def wait_host_outputs(self):
         """Block the host until the read-back started by the last ``step(..., host_out=...)`` has landed.  The device

@@ -206,11 +206,13 @@ def seeded_nbp_state_dict(net, seed: int = 9):
     return sd
 
 
-def calibrated_nbp(device, seed: int = 9, calib_S: int = 64, calib_B: int = 2):
+def calibrated_nbp(device, seed: int = 9, calib_S: int = 64, calib_B: int = 2, calib_x=None):
     """An eval-mode ``NBP`` on ``device`` with seeded weights whose BatchNorm running statistics are the batch statistics of
     count-like inputs (one train-mode pass with momentum 1 on the CUDA kernels) and whose value head is scaled so that the
     value map is O(1-10), like the x100 coverage gains the reference trains on (nbp_utils.py:668).  With default running
-    statistics activations explode / vanish and every accuracy figure would be meaningless."""
+    statistics activations explode / vanish and every accuracy figure would be meaningless.
+    ``calib_x`` (B,5,S,S): calibrate on these model inputs instead (e.g. grids of the workload about to be run -- what training on
+    that data would leave in the running statistics)."""
     import torch
     from .networks import NBP
     net = NBP()
@@ -219,14 +221,14 @@ def calibrated_nbp(device, seed: int = 9, calib_S: int = 64, calib_B: int = 2):
     net.train()
     net.bn_momentum = 1.0
     with torch.no_grad():
-        net(count_like_input(calib_B, calib_S, seed=seed + 1).to(device))
+        net(count_like_input(calib_B, calib_S, seed=seed + 1).to(device) if calib_x is None else calib_x.to(device))
     net.bn_momentum = 0.1
     net.eval()
     with torch.no_grad():
         for k, v in net.state_dict().items():
             if k.endswith("num_batches_tracked"):
                 v.zero_()
-        o1, _ = net(count_like_input(1, calib_S, seed=seed + 2).to(device))
+        o1, _ = net(count_like_input(1, calib_S, seed=seed + 2).to(device) if calib_x is None else calib_x[:1].to(device))
         scale = 5.0 / float(o1.abs().max().clamp_min(1e-6))
         net.Final1.weight.mul_(scale)
         net.Final1.bias.mul_(scale)

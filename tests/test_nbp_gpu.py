@@ -287,6 +287,9 @@ def test_nbp_fast_fp16_mode_error_is_as_documented():
     assert 1e-4 < l1 < 3e-2 and l2 < 5e-2
 
 
+ACT8 = 0.125          # NBP_E4M3_ACT_SCALE: the e4m3 planes hold x / 8
+
+
 def _e4m3(x):
     return x.clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
 
@@ -297,8 +300,8 @@ def _to_act_fmt2(x):
     a = x.permute(0, 2, 3, 1).contiguous()
     n, h, w, c = a.shape
     hi = a.to(torch.float16)
-    q_x = _e4m3(a).view(torch.uint8).view(n, h, w, c // 64, 1, 64)
-    q_lo = _e4m3((a - hi.float()) * 2048.0).view(torch.uint8).view(n, h, w, c // 64, 1, 64)
+    q_x = _e4m3(a * ACT8).view(torch.uint8).view(n, h, w, c // 64, 1, 64)
+    q_lo = _e4m3((a - hi.float()) * 2048.0 * ACT8).view(torch.uint8).view(n, h, w, c // 64, 1, 64)
     p8 = torch.cat((q_x, q_lo), dim=4).reshape(n, h, w, 2 * c).contiguous().view(torch.float16)
     return torch.cat((hi, p8), dim=-1).contiguous().to(DEV), c, 2 * c, c
 
@@ -310,7 +313,7 @@ def _from_act_fmt2(t, c):
     p8 = t[..., c:2 * c].contiguous().view(torch.uint8).view(*t.shape[:-1], c // 64, 2, 64)
     q_x = p8[..., 0, :].reshape(*t.shape[:-1], c).view(torch.float8_e4m3fn).float()
     q_lo = p8[..., 1, :].reshape(*t.shape[:-1], c).view(torch.float8_e4m3fn).float()
-    return hi + q_lo / 2048.0, q_x
+    return hi + q_lo / (2048.0 * ACT8), q_x / ACT8
 
 
 @pytest.mark.parametrize("n,h,w,c0,c1,cout,taps,up", [(2, 16, 16, 64, 0, 64, 9, 0), (1, 32, 32, 128, 0, 128, 9, 0), (3, 8, 8, 64, 0, 128, 9, 0),
@@ -348,8 +351,8 @@ def test_conv_fwd_e4m3_correction_mode(n, h, w, c0, c1, cout, taps, up):
     # ---- the mode's arithmetic in float64 on the quantised operands
     xd = x.double()
     xh = x.to(torch.float16).double()
-    x8 = _e4m3(x).double()
-    xl8 = _e4m3((x - x.to(torch.float16).float()) * 2048.0).double()
+    x8 = _e4m3(x * ACT8).double() / ACT8
+    xl8 = _e4m3((x - x.to(torch.float16).float()) * 2048.0 * ACT8).double() / ACT8
     conv = lambda inp, ww: F.conv2d(F.interpolate(inp, scale_factor=2, mode="nearest") if up else inp, ww, padding=k // 2)
     wh = wt.to(torch.float16)
     if up:        # quantisation applies to the pre-summed parity weights: evaluate the four parity convolutions explicitly
@@ -384,7 +387,7 @@ def test_conv_fwd_e4m3_correction_mode(n, h, w, c0, c1, cout, taps, up):
     assert rel(v1, exact) <= 1e-4                                  # ~15-bit operands
     assert rel(v2, want) <= 3e-5                                   # fmt-2 output keeps hi + e4m3 lo: 2^-15
     assert torch.equal(outs[2][..., :cout], outs[1][..., :cout])   # same hi plane in both formats
-    assert torch.equal(q2, _e4m3(v1).float().cpu()) or rel(q2, want) <= 4e-2     # e4m3 copy of the value (ties aside)
+    assert rel(q2, want) <= 4e-2                                   # the e4m3 copy of the value: 3 mantissa bits
 
 
 def test_nbp_graph_replay_equals_eager_and_tracks_inputs_and_weights():
