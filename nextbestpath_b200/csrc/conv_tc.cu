@@ -72,6 +72,7 @@ struct ConvKParams {
     int lo0, lo1;                       // element offset of the lo plane inside the tensor maps (PRECISE)
     float lo_scale;                     // acc = acc_hi + acc_lo * lo_scale (1/2048 for fp16x2, 1/(2048 s) for fp16+e4m3)
     int dst_fmt, pool_fmt;              // second-plane format written by the epilogue: 1 = fp16 lo*2048, 2 = e4m3 pair (MODE 2 consumers)
+    int interleave;                     // MODE 2: 1 = alternate the fp16 and e4m3 UMMAs per 16-element K step instead of issuing two runs
     unsigned long long* sat_count;      // optional: += number of (pixel, 32-channel group) stores in which an e4m3 value saturated
     int out_f32;                        // 1: the destination is plain fp32 NHWC (gradients), no fp16 planes
     int kchunk;                         // K stages accumulated inside TMEM before the partial sum is folded into fp32
@@ -222,6 +223,14 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                             const uint64_t alo = umma_desc_kmajor_sw128(a_addr + (uint32_t)((row0 + j) * p.aoff_step) + Cfg::A_PLANE);
                             const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr + (uint32_t)(j * Cfg::B_TILE_BYTES));
                             const uint64_t blo = umma_desc_kmajor_sw128(b_addr + (uint32_t)(j * Cfg::B_TILE_BYTES + BLOCK_N * BLOCK_K * 2));
+                            if (FP8 && !p.interleave) {
+#pragma unroll
+                                for (int k = 0; k < BLOCK_K / 16; ++k)
+                                    umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, (ks > ks0 || j > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                                for (int k = 0; k < BLOCK_K / 16; ++k)
+                                    umma_f8(d_tmem + (uint32_t)BLOCK_N, alo + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), idesc_lo, (ks > ks0 || j > 0 || k > 0) ? 1u : 0u);
+                            } else {
 #pragma unroll
                             for (int k = 0; k < BLOCK_K / 16; ++k) {
                                 const uint32_t accum = (ks > ks0 || j > 0 || k > 0) ? 1u : 0u;
@@ -233,25 +242,40 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                                     if (PRECISE) umma_f16(d_tmem + (uint32_t)BLOCK_N, alo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, 1u);
                                 }
                             }
+                            }
                         }
                     } else {
                     const uint64_t adesc = umma_desc_kmajor_sw128(a_addr);
                     const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr);
                     const uint64_t alo = umma_desc_kmajor_sw128(a_addr + A_STAGE_BYTES);
                     const uint64_t blo = umma_desc_kmajor_sw128(b_addr + BLOCK_N * BLOCK_K * 2);     // the e4m3 weight rows (MODE 2)
+                    if (FP8) {
+                        // hi product on the fp16 pipe, then both corrections as one K = 128 e4m3 reduction ([A_hi8 | A_lo8] . [W_lo8 ; W_hi8]);
+                        // the two kinds are issued as two runs (NBP_CONV_INTERLEAVE=1 alternates them instead: A/B switch, default off)
+                        if (!p.interleave) {
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k)
+                                umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, (ks > ks0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k)
+                                umma_f8(d_tmem + (uint32_t)BLOCK_N, alo + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), idesc_lo, (ks > ks0 || k > 0) ? 1u : 0u);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k) {
+                                const uint32_t accum = (ks > ks0 || k > 0) ? 1u : 0u;
+                                umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, accum);
+                                umma_f8(d_tmem + (uint32_t)BLOCK_N, alo + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), idesc_lo, accum);
+                            }
+                        }
+                    } else {
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; ++k) {
-                        // +32 bytes along K inside the 128-byte swizzle row (16 fp16 or 32 e4m3): +2 in the encoded address
+                        // +32 bytes along K inside the 128-byte swizzle row (16 fp16): +2 in the encoded address
                         const uint32_t accum = (ks > ks0 || k > 0) ? 1u : 0u;
-                        if (FP8) {
-                            // hi product on the fp16 pipe, both corrections as one K = 128 e4m3 reduction ([A_hi8 | A_lo8] . [W_lo8 ; W_hi8])
-                            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, accum);
-                            umma_f8(d_tmem + (uint32_t)BLOCK_N, alo + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), idesc_lo, accum);
-                        } else {
-                            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_main, accum);
-                            // A_lo * W_hi accumulates into the acc_lo columns that the UMMA above just wrote (in-order pipe)
-                            if (PRECISE) umma_f16(d_tmem + (uint32_t)BLOCK_N, alo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, 1u);
-                        }
+                        umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_main, accum);
+                        // A_lo * W_hi accumulates into the acc_lo columns that the UMMA above just wrote (in-order pipe)
+                        if (PRECISE) umma_f16(d_tmem + (uint32_t)BLOCK_N, alo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, 1u);
+                    }
                     }
                     }
                     umma_commit(&empty_bar[stage]);           // frees the smem slot once these MMAs have read it
@@ -579,10 +603,15 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     kp.out_f32 = d->out_f32 ? 1 : 0;
     // ---- vertical halo reuse (64- and 32-channel tiles, whose K steps are too short to hide the operand latency): tiles inside one
     // image whose rows are whole 8-pixel swizzle groups; training's short accumulation chains (k_chunk 1..2) keep the plain path
-    static int halo_env = -1, kchunk_env = -1;
+    static int halo_env = -1, kchunk_env = -1, inter_env = -1, k8_env = -1;
+    if (inter_env < 0) { const char* e = getenv("NBP_CONV_INTERLEAVE"); inter_env = e ? atoi(e) : 0; }
+    if (k8_env < 0) { const char* e = getenv("NBP_CONV_KCHUNK_E4M3"); k8_env = e ? atoi(e) : 0; }
+    kp.interleave = inter_env;
     if (halo_env < 0) { const char* e = getenv("NBP_CONV_HALO"); halo_env = e ? atoi(e) : 1; }
     if (kchunk_env < 0) { const char* e = getenv("NBP_CONV_KCHUNK"); kchunk_env = e ? atoi(e) : 8; }
-    const int want = d->k_chunk > 0 ? d->k_chunk : kchunk_env;       // K slices (64 elements each) per in-TMEM accumulation chain; 0 = unbounded
+    // K slices (64 elements each) per in-TMEM accumulation chain; 0 = unbounded.  The fp16+e4m3 mode keeps whole reductions in TMEM by
+    // default: the truncating accumulator costs 1.2e-9 * K relative (1.1e-5 at K = 9216), an order below that mode's operand error
+    const int want = d->k_chunk > 0 ? d->k_chunk : (fp8 ? k8_env : kchunk_env);
     const bool halo = halo_env && precise && block_n <= 64 && (d->taps == 9 || d->up2x) && kp.tn == 1 && kp.tw >= 8 &&
                       (kp.th + 2) * kp.tw <= HALO_ROWS && !(want > 0 && want < 3);
     const int planes_ = precise ? 2 : 1;

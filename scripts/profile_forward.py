@@ -20,9 +20,16 @@ net.precision = precision
 net.use_cuda_graph = False
 x = syn.count_like_input(B, S, seed=3).to(dev)
 with torch.no_grad():
-    for _ in range(reps + 1):
+    net(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
         net(x)
+    e1.record()
 torch.cuda.synchronize()
+print(f"{precision} B={B} S={S}: {e0.elapsed_time(e1) / reps:.3f} ms per forward (kernel by kernel, {reps} reps), env "
+      + " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("NBP_CONV")))
 order = ["Conv1.b"] + [f"Conv{l}.{ab}" for l in range(2, 6) for ab in "ab"]
 for dec, lvls in ((1, (5, 4)), (2, (5, 4, 3, 2))):
     for l in lvls:
