@@ -87,6 +87,14 @@ def max_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
+class _null_ctx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
 STAGE_NAMES = ("A_backproject_key", "B_grid_scatter", "C_nbp_forward", "D_render_4_views", "E_backproject_4_frames")
 
 
@@ -138,6 +146,9 @@ class RolloutEngine:
         self._uid_base = torch.arange(B, dtype=torch.int32, device=dev) * 8
         self._copy_stream = None        # side stream of the device->host read-back (created on first use)
         self._copy_done = None
+        self.overlap_geometry = True    # stages D/E on a side stream under stage C (see step)
+        self._geo_stream = None
+        self._after_b = None
 
     def set_network(self, nbp):
         """The engine consumes (or copies out) the maps of a step before it runs the next forward: NBP.forward may hand out the
@@ -239,6 +250,8 @@ class RolloutEngine:
                              traj_len=self.traj_len, n_pieces=self.n_pieces, grid_range=self.grid_range,
                              max_points=self.max_points_bound, out=self.grid)
             mark()
+            if self.overlap_geometry:
+                self._after_b = torch.cuda.Event(); self._after_b.record()
             # ---- C: network
             if self._copy_done is not None:                      # the previous step's read-back still owns the output buffers
                 torch.cuda.current_stream(self.dev).wait_event(self._copy_done)
@@ -257,19 +270,34 @@ class RolloutEngine:
                         h.copy_(d, non_blocking=True)
                         d.record_stream(self._copy_stream)
                     self._copy_done.record()
-        # ---- D: move + render 4 frames straight into slots 1..4 (slot 4 is the new key frame)
-        self._render(R4, T4, self.view_scene4, self.view_scene4_host, self.frames[1:5].view(4 * B, H, W))
-        self.frame_R[1:5].copy_(R4.view(4, B, 9)); self.frame_T[1:5].copy_(T4.view(4, B, 3))
-        self._append_traj(poses4[:, :, :3].permute(1, 0, 2))
-        mark()
-        # ---- E: back-project [old key, interp1, interp2, interp3]; frames of a scene append in slot order
-        ops.backproject_append(self.frames[0:4].view(4 * B, H, W), self.frame_R[0:4].view(4 * B, 9), self.frame_T[0:4].view(4 * B, 3),
-                               self.view_scene4, self.cloud, self.cloud_len, frame_uid=self._uids(4, 1),
-                               fov_range=self.sensor_range, gathering_factor=self.gf, seed=self.seed, overflow=self.overflow)
-        self.max_points_bound = min(self.cap, self.max_points_bound + 4 * n_new)
-        # ---- the new key frame becomes slot 0
-        self.frames[0].copy_(self.frames[4]); self.frame_R[0].copy_(self.frame_R[4]); self.frame_T[0].copy_(self.frame_T[4])
-        self.pose.copy_(poses4[3])
-        mark()
+        # ---- D + E do not depend on the network (the move was decided before the step): they run on a side stream UNDER stage C --
+        # issue- / HBM-bound geometry kernels filling the tail waves of the tensor-bound network -- and rejoin the main stream at the
+        # end of the step (``overlap_geometry=False`` keeps everything on one stream)
+        main = torch.cuda.current_stream(self.dev)
+        side = None
+        if self.overlap_geometry and run_network:
+            if self._geo_stream is None:
+                self._geo_stream = torch.cuda.Stream(device=self.dev)
+            side = self._geo_stream
+            side.wait_event(self._after_b)
+        with torch.cuda.stream(side) if side is not None else _null_ctx():
+            # ---- D: move + render 4 frames straight into slots 1..4 (slot 4 is the new key frame)
+            self._render(R4, T4, self.view_scene4, self.view_scene4_host, self.frames[1:5].view(4 * B, H, W))
+            self.frame_R[1:5].copy_(R4.view(4, B, 9)); self.frame_T[1:5].copy_(T4.view(4, B, 3))
+            self._append_traj(poses4[:, :, :3].permute(1, 0, 2))
+            mark()
+            # ---- E: back-project [old key, interp1, interp2, interp3]; frames of a scene append in slot order
+            ops.backproject_append(self.frames[0:4].view(4 * B, H, W), self.frame_R[0:4].view(4 * B, 9), self.frame_T[0:4].view(4 * B, 3),
+                                   self.view_scene4, self.cloud, self.cloud_len, frame_uid=self._uids(4, 1),
+                                   fov_range=self.sensor_range, gathering_factor=self.gf, seed=self.seed, overflow=self.overflow)
+            self.max_points_bound = min(self.cap, self.max_points_bound + 4 * n_new)
+            # ---- the new key frame becomes slot 0
+            self.frames[0].copy_(self.frames[4]); self.frame_R[0].copy_(self.frame_R[4]); self.frame_T[0].copy_(self.frame_T[4])
+            self.pose.copy_(poses4[3])
+            mark()
+            if side is not None:
+                done = torch.cuda.Event(); done.record(side)
+        if side is not None:
+            main.wait_event(done)
         self.step_idx += 1
         return StepOutput(out1, out2, vmax, self.grid) if run_network else None

@@ -139,6 +139,32 @@ def test_rollout_subsampled_statistics():
     assert runs[0][2][:, :4].sum() > 0
 
 
+def test_rollout_geometry_overlap_is_invisible():
+    """Stages D/E on a side stream under the network (the default) give the same clouds, grids and maps, bit for bit, as the
+    single-stream order."""
+    B, n_steps = 3, 3
+    scenes = [syn.make_scene(65 + i, tri_budget=900) for i in range(B)]
+    walks = [syn.random_walk(sc, n_steps + 1, seed=95 + i) for i, sc in enumerate(scenes)]
+    poses = np.stack([w[0] for w in walks]); az = np.stack([w[1] for w in walks])
+    net = NBP(); net.load_state_dict(NT.golden_state_dict(seed=9)); net.to(DEV).eval()
+    runs = []
+    for overlap in (True, False):
+        eng = RolloutEngine(scenes, net, DEV, S=S, H=H, W=W, max_steps=n_steps + 1, gathering_factor=0.05, seed=4)
+        eng.overlap_geometry = overlap
+        eng.reset(poses[:, 0])
+        outs = []
+        for t in range(n_steps):
+            o = eng.step(eng.upload_move(poses[:, t], poses[:, t + 1], az[:, t], az[:, t + 1]))
+            outs.append((o.model_input.clone(), o.value_map.clone(), o.obstacle_map.clone()))
+        torch.cuda.synchronize()
+        runs.append((eng.cloud_len.cpu(), eng.cloud.cpu(), eng.frames.cpu(), outs))
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][2], runs[1][2])
+    n = int(runs[0][0].max())
+    assert torch.equal(runs[0][1][:, :n], runs[1][1][:, :n])
+    for a, b in zip(runs[0][3], runs[1][3]):
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
 def test_rollout_host_outputs_overlap_copy():
     """step(..., host_out=...) reads the maps back on a side stream under stages D/E: the pinned host buffers hold the
     same bits as the device outputs once wait_host_outputs() returns, and the engine state is unaffected."""
