@@ -225,7 +225,7 @@ def run_ours(args):
     n_total = args.prefill + 2 * (args.warmup + args.steps) + (args.steps + 1) + 4
     scenes, poses, az = make_workload(B, args.level, n_total + 8, rank0_scene_index=first)
     eng = RolloutEngine(scenes, None, dev, S=S, max_steps=n_total + 1, seed=9)
-    eng.overlap_geometry = not args.no_overlap
+    eng.overlap_geometry = args.overlap
     eng.reset(poses[:, 0])
     t = 0
     for _ in range(args.prefill):                                   # geometry-only fast-forward to pose `prefill`
@@ -292,7 +292,7 @@ def run_ours(args):
     eng.overlap_geometry = False                                   # the diagnostic wants the stages back to back on one stream
     eng.step(eng.upload_move(poses[:, t], poses[:, t + 1], az[:, t], az[:, t + 1]))
     torch.cuda.synchronize()
-    eng.overlap_geometry = not args.no_overlap
+    eng.overlap_geometry = args.overlap
     evs = eng.stage_events
     eng.stage_events = None
     stage_ms = {nm: evs[i].elapsed_time(evs[i + 1]) for i, nm in enumerate(STAGE_NAMES)}
@@ -411,7 +411,7 @@ def run_ours(args):
                        "mean_faces_per_scene": mean_faces, "prefill_pose": args.prefill,
                        "mean_cloud_points_per_scene_at_start": cloud_pts, "nbp_chunk": args.chunk, "precision": args.precision,
                        "network_launch": "CUDA graph replay (captured once per shape)",
-                       "geometry_overlap": "stages D/E on a side stream under stage C" if not args.no_overlap else "off (single stream)",
+                       "geometry_overlap": "stages D/E on a side stream under stage C" if args.overlap else "off (single stream)",
                        "weights": "seeded (no checkpoints offline); BatchNorm statistics calibrated on 8 model inputs of this workload",
                        "l2": "inputs larger than L2 (per-step working set > 5 GB: clouds, frames, activations)",
                        "parallelism": f"scenes sharded over {world} rank(s), no collective"},
@@ -571,7 +571,7 @@ def main():
     ap.add_argument("--precision", default="mixed", choices=["mixed", "fp16x2", "fp16"])
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="run stages D/E on the main stream instead of under the network")
+    ap.add_argument("--overlap", action="store_true", help="run stages D/E on a side stream under the network (measured: no gain)")
     ap.add_argument("--no-extras", action="store_true", help="skip the latency_b1 / cudnn_baseline / train blocks")
     ap.add_argument("--train-tiles", type=int, default=64, help="tiles per GPU per optimizer step of the train block")
     ap.add_argument("--train-micro", type=int, default=32)

@@ -140,8 +140,8 @@ def test_rollout_subsampled_statistics():
 
 
 def test_rollout_geometry_overlap_is_invisible():
-    """Stages D/E on a side stream under the network (the default) give the same clouds, grids and maps, bit for bit, as the
-    single-stream order."""
+    """Stages D/E on a side stream under the network (RolloutEngine.overlap_geometry) give the same clouds, grids and maps, bit
+    for bit, as the single-stream order."""
     B, n_steps = 3, 3
     scenes = [syn.make_scene(65 + i, tri_budget=900) for i in range(B)]
     walks = [syn.random_walk(sc, n_steps + 1, seed=95 + i) for i, sc in enumerate(scenes)]
