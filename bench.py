@@ -274,11 +274,16 @@ def run_ours(args):
     barrier()
     launches0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof = os.environ.get("NBP_BENCH_CUDA_PROFILER") == "1"         # ncu/nsys --profile-from-start off: capture exactly the timed steps
+    if prof:
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(args.warmup, n_run):
         eng.step(moves[i])
     e1.record()
     barrier()
+    if prof:
+        torch.cuda.profiler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = ops.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
