@@ -23,11 +23,13 @@ with torch.no_grad():
     net(x)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()          # ncu --profile-from-start off: only the forwards below are captured
     e0.record()
     for _ in range(reps):
         net(x)
     e1.record()
-torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
 print(f"{precision} B={B} S={S}: {e0.elapsed_time(e1) / reps:.3f} ms per forward (kernel by kernel, {reps} reps), env "
       + " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("NBP_CONV")))
 order = ["Conv1.b"] + [f"Conv{l}.{ab}" for l in range(2, 6) for ab in "ab"]
