@@ -4,12 +4,15 @@
 // growing torch.vstack at next_best_path/testers/nbp_planning.py:105,352.
 //
 // Three launches per call, one CTA (1024 threads) per frame in the two heavy ones:
-//   bp_select : count the n valid pixels; if k = int(n*gf) < n, radix-select (9-bit digits, shared
-//               histogram) the k-th smallest key of a keyed Feistel bijection of the pixel index.
+//   bp_select : n = valid pixels, k = int(n*gf); if k < n, radix-select (9-bit digits, shared histogram; the first
+//               pass doubles as the count) the k-th smallest key of a keyed Feistel bijection of the pixel index.
 //   bp_offsets: per-frame append offsets (frames of one scene append in frame order) + new cloud_len.
-//   bp_write  : ordered compaction of the selected pixels, closed-form un-projection
-//               (oracle/oracle.py::unproject is the pin: one fp32 rounding per op), float stores.
-// zbuf is read 4x but only the first read comes from HBM (467 KB per frame stays in the 126 MB L2).
+//   bp_write  : ordered compaction of the selected pixels (keep / drop decided once, cached as 4-bit masks in
+//               registers), closed-form un-projection (oracle/oracle.py::unproject is the pin: one fp32 rounding
+//               per op), float stores.
+// Pixels are read four at a time (16-byte loads, four independent Feistel chains per thread): round 1's scalar loops
+// were latency-bound at IPC 0.5 (profiles/r02_geometry_ncu_full.txt).  zbuf is read 3x (2 select passes + write), only
+// the first read comes from HBM (467 KB per frame stays in the 126 MB L2).
 #include "nbp_common.cuh"
 
 namespace nbp {
@@ -58,74 +61,108 @@ struct BpParams {
     FrameSel* sel;
 };
 
-__device__ __forceinline__ bool pixel_valid(const BpParams& p, const float* z, const uint8_t* m, int i) {
-    const float d = __ldg(z + i);
-    bool v = m ? (m[i] != 0) : (d > -1.0f);       // an explicit mask replaces the default zbuf > -1 (macarons_utils.py:2771,2825)
+__device__ __forceinline__ bool depth_valid(const BpParams& p, float d, bool masked_in) {
+    bool v = masked_in;                            // an explicit mask replaces the default zbuf > -1 (macarons_utils.py:2771,2825)
     if (p.fov_range > 0.0f) v = v && (d < p.fov_range);
     return v;
 }
 
+__device__ __forceinline__ bool pixel_valid(const BpParams& p, const float* z, const uint8_t* m, int i) {
+    const float d = __ldg(z + i);
+    return depth_valid(p, d, m ? (m[i] != 0) : (d > -1.0f));
+}
+
+// validity of the 4 consecutive pixels 4q .. 4q+3 as a bit mask (one 16-byte load; frames are 16-byte aligned when HW % 4 == 0)
+__device__ __forceinline__ unsigned quad_valid(const BpParams& p, const float* z, const uint8_t* m, int q, float* d4) {
+    const float4 d = __ldg(reinterpret_cast<const float4*>(z) + q);
+    d4[0] = d.x; d4[1] = d.y; d4[2] = d.z; d4[3] = d.w;
+    unsigned in = 0;
+    if (m) {
+        const uchar4 mm = *reinterpret_cast<const uchar4*>(m + 4 * (size_t)q);
+        in = (mm.x != 0) | ((mm.y != 0) << 1) | ((mm.z != 0) << 2) | ((mm.w != 0) << 3);
+    } else {
+        in = (d.x > -1.0f) | ((d.y > -1.0f) << 1) | ((d.z > -1.0f) << 2) | ((d.w > -1.0f) << 3);
+    }
+    unsigned v = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v |= (depth_valid(p, d4[j], (in >> j) & 1u) ? 1u : 0u) << j;
+    return v;
+}
+
+// Per frame: n = number of valid pixels, k = int(n * gf), and -- when k < n -- the k-th smallest key tau of a keyed bijection of the
+// pixel index (radix select, 9-bit digits, shared histogram): exactly k valid pixels have key <= tau.  The first radix pass doubles as
+// the count (n = sum of its histogram); pixels are read four at a time so that four independent Feistel chains are in flight per thread.
 __global__ void __launch_bounds__(BP_THREADS) bp_select(BpParams p) {
     __shared__ int s_hist[512];
     __shared__ int s_red[BP_THREADS / 32];
-    __shared__ uint32_t s_prefix; __shared__ int s_krem; __shared__ int s_n;
+    __shared__ uint32_t s_prefix; __shared__ int s_krem; __shared__ int s_n; __shared__ int s_k;
 
     const int f = blockIdx.x;
     const float* z = p.zbuf + (size_t)f * p.HW;
     const uint8_t* m = p.mask ? p.mask + (size_t)f * p.HW : nullptr;
-
-    // ---- count valid
-    int cnt = 0;
-    for (int i = threadIdx.x; i < p.HW; i += BP_THREADS) cnt += pixel_valid(p, z, m, i) ? 1 : 0;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-    if (lane_id() == 0) s_red[threadIdx.x >> 5] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int n = 0;
-        for (int w = 0; w < BP_THREADS / 32; ++w) n += s_red[w];
-        s_n = n;
-    }
-    __syncthreads();
-    const int n = s_n;
-    int k = (p.gf >= 1.0) ? n : (int)((double)n * p.gf);
-    if (k > n) k = n;
-    if (k < 0) k = 0;
+    const bool vec = (p.HW & 3) == 0;
+    const int nq = vec ? p.HW >> 2 : 0;                       // quads; the scalar loop below covers everything when !vec
+    const bool subsample = p.gf < 1.0;
+    const Feistel perm = make_feistel(p.seed, p.frame_uid ? p.frame_uid[f] : f, p.key_bits);
 
     uint32_t tau = 0xffffffffu;
-    if (k > 0 && k < n) {
-        const Feistel perm = make_feistel(p.seed, p.frame_uid ? p.frame_uid[f] : f, p.key_bits);
-        if (threadIdx.x == 0) { s_prefix = 0; s_krem = k; }
-        int bits_left = p.key_bits;
-        while (bits_left > 0) {
-            const int db = bits_left >= 9 ? 9 : bits_left;       // digit width of this pass
-            const int shift = bits_left - db;
-            for (int b = threadIdx.x; b < 512; b += BP_THREADS) s_hist[b] = 0;
-            __syncthreads();
-            const uint32_t prefix = s_prefix;                    // already-fixed high bits (aligned at `bits_left`)
-            for (int i = threadIdx.x; i < p.HW; i += BP_THREADS) {
-                if (!pixel_valid(p, z, m, i)) continue;
-                const uint32_t key = perm((uint32_t)i);
-                if ((key >> bits_left) != prefix) continue;
-                atomicAdd(&s_hist[(key >> shift) & ((1u << db) - 1u)], 1);
+    int bits_left = p.key_bits;
+    bool first = true;
+    if (threadIdx.x == 0) { s_prefix = 0; s_krem = 0; s_k = 0; }
+    do {
+        const int db = bits_left >= 9 ? 9 : bits_left;       // digit width of this pass
+        const int shift = bits_left - db;
+        for (int b = threadIdx.x; b < 512; b += BP_THREADS) s_hist[b] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;                    // already-fixed high bits (aligned at `bits_left`)
+        int cnt = 0;
+        auto visit = [&](int i) {
+            if (!subsample) { ++cnt; return; }
+            const uint32_t key = perm((uint32_t)i);
+            if ((key >> bits_left) != prefix) return;
+            atomicAdd(&s_hist[(key >> shift) & ((1u << db) - 1u)], 1);
+        };
+        for (int q = threadIdx.x; q < nq; q += BP_THREADS) {
+            float d4[4];
+            const unsigned v = quad_valid(p, z, m, q, d4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if ((v >> j) & 1u) visit(4 * q + j);
+        }
+        if (!vec) for (int i = threadIdx.x; i < p.HW; i += BP_THREADS) if (pixel_valid(p, z, m, i)) visit(i);
+        if (first && !subsample) {                           // keep everything: only the count is needed
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+            if (lane_id() == 0) s_red[threadIdx.x >> 5] = cnt;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int nb = 1 << db;
+            if (first) {
+                int n = 0;
+                if (subsample) for (int d = 0; d < nb; ++d) n += s_hist[d];
+                else for (int w = 0; w < BP_THREADS / 32; ++w) n += s_red[w];
+                int k = subsample ? (int)((double)n * p.gf) : n;
+                if (k > n) k = n;
+                if (k < 0) k = 0;
+                s_n = n; s_k = k; s_krem = k;
             }
-            __syncthreads();
-            if (threadIdx.x == 0) {
+            if (subsample && s_k > 0 && s_k < s_n) {
                 int krem = s_krem, acc = 0, d = 0;
-                const int nb = 1 << db;
                 for (; d < nb; ++d) {
                     if (acc + s_hist[d] >= krem) break;
                     acc += s_hist[d];
                 }
-                if (d >= nb) d = nb - 1;                          // cannot happen (k <= n)
+                if (d >= nb) d = nb - 1;                      // cannot happen (k <= n)
                 s_krem = krem - acc;
                 s_prefix = (prefix << db) | (uint32_t)d;
             }
-            __syncthreads();
-            bits_left = shift;
         }
-        tau = s_prefix;     // keys are unique: exactly k valid pixels have key <= tau
-    }
+        __syncthreads();
+        first = false;
+        bits_left = shift;
+    } while (subsample && bits_left > 0 && s_k > 0 && s_k < s_n);
+    const int n = s_n, k = s_k;
+    if (subsample && k > 0 && k < n) tau = s_prefix;         // keys are unique: exactly k valid pixels have key <= tau
     if (threadIdx.x == 0) {
         FrameSel s; s.n = n; s.k = k; s.tau = tau; s.base = 0; s.final_len = -1; s.pad[0] = s.pad[1] = s.pad[2] = 0;
         p.sel[f] = s;
@@ -152,6 +189,22 @@ __global__ void bp_offsets(BpParams p) {
     }
 }
 
+static constexpr int BP_MASK_WORDS = 8;        // 4-bit keep masks of 8 quads per word: a warp range of up to 8 * 8 * 128 = 8192 pixels stays in registers
+
+__device__ __forceinline__ void unproject_store(const BpParams& p, const float* sR, const float* sT, int i, float d, float* o) {
+    const int row = i / p.W, col = i - row * p.W;
+    // NDC tables of macarons_utils.py:2270-2279
+    const float nx = fsub(p.wm, fmul(fdiv((float)col, p.mm1), 2.0f));
+    const float ny = fsub(p.hm, fmul(fdiv((float)row, p.mm1), 2.0f));
+    const float sc = fmul(d, p.tan_half);
+    const float dx = fsub(fmul(nx, sc), sT[0]);
+    const float dy = fsub(fmul(ny, sc), sT[1]);
+    const float dz = fsub(d, sT[2]);
+    o[0] = fadd(fadd(fmul(dx, sR[0]), fmul(dy, sR[1])), fmul(dz, sR[2]));
+    o[1] = fadd(fadd(fmul(dx, sR[3]), fmul(dy, sR[4])), fmul(dz, sR[5]));
+    o[2] = fadd(fadd(fmul(dx, sR[6]), fmul(dy, sR[7])), fmul(dz, sR[8]));
+}
+
 __global__ void __launch_bounds__(BP_THREADS) bp_write(BpParams p) {
     __shared__ int s_wcnt[BP_THREADS / 32];
     __shared__ float sR[9], sT[3];
@@ -169,49 +222,91 @@ __global__ void __launch_bounds__(BP_THREADS) bp_write(BpParams p) {
     const bool all = sel.k == sel.n;
     const Feistel perm = make_feistel(p.seed, p.frame_uid ? p.frame_uid[f] : f, p.key_bits);
     float* out = p.cloud + (size_t)scene * (size_t)p.cap * 3;
-
-    // every warp owns one contiguous range of pixels (row-major order is preserved): two passes over the range, the
-    // first counts the kept pixels, the second writes them at (frame base + ranges before + rank inside the range).
-    // Only two block-wide barriers per frame.
     const int warp = threadIdx.x >> 5, lane = lane_id(), nwarp = BP_THREADS / 32;
-    const int per = (((p.HW + nwarp - 1) / nwarp) + 31) & ~31;
-    const int i0 = warp * per, i1 = min(p.HW, i0 + per);
-    int cnt = 0;
-    for (int b = i0; b < i1; b += 32) {
-        const int i = b + lane;
-        const bool keep = i < i1 && pixel_valid(p, z, m, i) && (all || perm((uint32_t)i) <= sel.tau);
-        cnt += __popc(__ballot_sync(0xffffffffu, keep));
-    }
-    if (lane == 0) s_wcnt[warp] = cnt;
-    __syncthreads();
-    int running = sel.base;
-    for (int w = 0; w < warp; ++w) running += s_wcnt[w];
-
-    const float wm = p.wm, hm = p.hm, mm1 = p.mm1;
     int dropped = 0;
-    for (int b = i0; b < i1; b += 32) {
-        const int i = b + lane;
-        const bool keep = i < i1 && pixel_valid(p, z, m, i) && (all || perm((uint32_t)i) <= sel.tau);
-        const unsigned ball = __ballot_sync(0xffffffffu, keep);
-        const int slot = running + __popc(ball & ((1u << lane) - 1u));
-        running += __popc(ball);
-        if (keep) {
-            if (slot < p.cap) {
-                const int row = i / p.W, col = i - row * p.W;
-                const float d = z[i];
-                // NDC tables of macarons_utils.py:2270-2279
-                const float nx = fsub(wm, fmul(fdiv((float)col, mm1), 2.0f));
-                const float ny = fsub(hm, fmul(fdiv((float)row, mm1), 2.0f));
-                const float sc = fmul(d, p.tan_half);
-                const float dx = fsub(fmul(nx, sc), sT[0]);
-                const float dy = fsub(fmul(ny, sc), sT[1]);
-                const float dz = fsub(d, sT[2]);
-                float* o = out + (size_t)slot * 3;
-                o[0] = fadd(fadd(fmul(dx, sR[0]), fmul(dy, sR[1])), fmul(dz, sR[2]));
-                o[1] = fadd(fadd(fmul(dx, sR[3]), fmul(dy, sR[4])), fmul(dz, sR[5]));
-                o[2] = fadd(fadd(fmul(dx, sR[6]), fmul(dy, sR[7])), fmul(dz, sR[8]));
-            } else {
-                ++dropped;
+
+    // every warp owns one contiguous range of pixels (row-major order is preserved).  Fast path: a lane reads 4 consecutive pixels per
+    // iteration (one 16-byte load), decides keep / drop ONCE (validity + key <= tau), remembers the 4-bit decisions in registers, and after
+    // the block-wide scan of the per-warp counts writes the kept pixels at (frame base + ranges before + rank inside the range).
+    const int per_q = ((((p.HW >> 2) + nwarp - 1) / nwarp) + 31) & ~31;            // quads per warp range
+    if ((p.HW & 3) == 0 && per_q <= BP_MASK_WORDS * 8 * 32) {
+        const int q0 = warp * per_q, q1 = min(p.HW >> 2, q0 + per_q);
+        uint32_t keep[BP_MASK_WORDS];
+#pragma unroll
+        for (int w = 0; w < BP_MASK_WORDS; ++w) keep[w] = 0;
+        const int n_it = per_q >> 5;                                                 // block-uniform; empty tail iterations are skipped
+        int cnt = 0;
+#pragma unroll
+        for (int it = 0; it < BP_MASK_WORDS * 8; ++it) {
+            if (it >= n_it) break;
+            const int q = q0 + it * 32 + lane;
+            unsigned mk = 0;
+            if (q < q1) {
+                float d4[4];
+                mk = quad_valid(p, z, m, q, d4);
+                if (!all) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (((mk >> j) & 1u) && perm((uint32_t)(4 * q + j)) > sel.tau) mk &= ~(1u << j);
+                }
+            }
+            keep[it >> 3] |= mk << (4 * (it & 7));
+            cnt += __popc(mk);
+        }
+        int wtot = cnt;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) wtot += __shfl_xor_sync(0xffffffffu, wtot, d);
+        if (lane == 0) s_wcnt[warp] = wtot;
+        __syncthreads();
+        int running = sel.base;
+        for (int w = 0; w < warp; ++w) running += s_wcnt[w];
+#pragma unroll
+        for (int it = 0; it < BP_MASK_WORDS * 8; ++it) {
+            if (it >= n_it) break;
+            const unsigned mk = (keep[it >> 3] >> (4 * (it & 7))) & 15u;
+            const int c = __popc(mk);
+            int incl = c;                                                            // inclusive scan of the lane counts of this iteration
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+            const int tot = __shfl_sync(0xffffffffu, incl, 31);
+            if (mk) {
+                const int q = q0 + it * 32 + lane;
+                const float4 d = __ldg(reinterpret_cast<const float4*>(z) + q);
+                const float dd[4] = {d.x, d.y, d.z, d.w};
+                int slot = running + incl - c;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if ((mk >> j) & 1u) {
+                        if (slot < p.cap) unproject_store(p, sR, sT, 4 * q + j, dd[j], out + (size_t)slot * 3);
+                        else ++dropped;
+                        ++slot;
+                    }
+                }
+            }
+            running += tot;
+        }
+    } else {
+        // general path (odd frame sizes / very large frames): two passes over the range, the first counts, the second writes
+        const int per = (((p.HW + nwarp - 1) / nwarp) + 31) & ~31;
+        const int i0 = warp * per, i1 = min(p.HW, i0 + per);
+        int cnt = 0;
+        for (int b = i0; b < i1; b += 32) {
+            const int i = b + lane;
+            const bool kp = i < i1 && pixel_valid(p, z, m, i) && (all || perm((uint32_t)i) <= sel.tau);
+            cnt += __popc(__ballot_sync(0xffffffffu, kp));
+        }
+        if (lane == 0) s_wcnt[warp] = cnt;
+        __syncthreads();
+        int running = sel.base;
+        for (int w = 0; w < warp; ++w) running += s_wcnt[w];
+        for (int b = i0; b < i1; b += 32) {
+            const int i = b + lane;
+            const bool kp = i < i1 && pixel_valid(p, z, m, i) && (all || perm((uint32_t)i) <= sel.tau);
+            const unsigned ball = __ballot_sync(0xffffffffu, kp);
+            const int slot = running + __popc(ball & ((1u << lane) - 1u));
+            running += __popc(ball);
+            if (kp) {
+                if (slot < p.cap) unproject_store(p, sR, sT, i, z[i], out + (size_t)slot * 3);
+                else ++dropped;
             }
         }
     }

@@ -13,12 +13,14 @@ NBP_BENCH_CUDA_PROFILER=1 ncu --profile-from-start off --set full --import-sourc
     -k regex:'grid_scatter|bp_select|bp_write|raster_tiles|raster_setup' -c 8 \
     -o $OUT/r02_geometry_full -f python bench.py --scenes 32 --steps 2 --warmup 3 --no-extras --no-cpu-baseline > $OUT/r02_geometry_full.log 2>&1
 ncu -i $OUT/r02_geometry_full.ncu-rep --page raw --csv > $OUT/r02_geometry_full_raw.csv 2>/dev/null
+rm -f $OUT/r02_geometry_full.ncu-rep
 if [ "$1" = "geometry-only" ]; then ls -la $OUT | grep r02_ | tail; exit 0; fi
 fi
 if true; then
 # (c) the conv kernel, all 33 layers of one 32-scene forward in the mixed precision, full set
-ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:conv_gemm -c 33 -o $OUT/r02_conv_full -f \
+ncu --profile-from-start off --set full --clock-control none -k regex:conv_gemm -c 33 -o $OUT/r02_conv_full -f \
     python scripts/profile_forward.py mixed 32 256 1 > $OUT/r02_conv_full.log 2>&1
 ncu -i $OUT/r02_conv_full.ncu-rep --page raw --csv > $OUT/r02_conv_full_raw.csv 2>/dev/null
+rm -f $OUT/r02_conv_full.ncu-rep            # 80+ MB: gpurun only copies back 64 MiB; the raw page above is what the summaries are made from
 fi
 ls -la $OUT | grep r02_ | tail -12
