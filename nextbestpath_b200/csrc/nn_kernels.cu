@@ -80,11 +80,15 @@ __device__ __forceinline__ void store8(__half* pix, int ch, int lo, int fmt, con
 }
 
 // ------------------------------------------------------------------------------------------------ conv_first
+// 8 lanes per pixel, 8 output channels per lane: the 8 lanes of a pixel read the same inputs (one broadcast transaction), disjoint
+// 32-byte weight chunks from shared memory, and store 128 contiguous bytes per plane (round 1: one thread per pixel writing 512
+// scattered bytes in 16-byte pieces -- 5x off the kernel's HBM roofline, profiles/r02_launches_two_steps_32scenes.txt).
 template <int COUT>
-__global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict__ x, int n, int cin, int h, int w,
+__global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, int n, int cin, int h, int w,
                                                          const float* __restrict__ wt,      // [9*cin][COUT]
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                                          __half* __restrict__ dst, int dst_ld, int dst_lo, int relu, int fmt) {
+    static_assert(COUT == 64, "8 lanes x 8 channels");
     extern __shared__ float s_w[];                    // 9*cin*COUT weights, then scale, shift
     const int nw = 9 * cin * COUT;
     for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = wt[i];
@@ -93,13 +97,15 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict
     __syncthreads();
     const size_t hw = (size_t)h * w;
     const size_t total = (size_t)n * hw;
-    for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = threadIdx.x & 7;                   // this lane's channel octet
+    const size_t first = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3, stride = ((size_t)gridDim.x * blockDim.x) >> 3;
+    for (size_t pix = first; pix < total; pix += stride) {
         const int img = (int)(pix / hw);
         const int rem = (int)(pix - (size_t)img * hw);
         const int y = rem / w, xx = rem - y * w;
-        float acc[COUT];
+        float acc[8];
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) acc[c] = 0.0f;
+        for (int c = 0; c < 8; ++c) acc[c] = 0.0f;
         const float* xin = x + (size_t)img * cin * hw;
         for (int tap = 0; tap < 9; ++tap) {
             const int yy = y + tap / 3 - 1, xc = xx + tap % 3 - 1;
@@ -107,29 +113,20 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict
             for (int ci = 0; ci < cin; ++ci) {
                 const float v = __ldg(xin + (size_t)ci * hw + (size_t)yy * w + xc);
                 if (v == 0.0f) continue;                         // count images are sparse
-                const float4* wr = reinterpret_cast<const float4*>(s_w + (tap * cin + ci) * COUT);
-#pragma unroll
-                for (int c4 = 0; c4 < COUT / 4; ++c4) {
-                    const float4 q = wr[c4];
-                    acc[4 * c4 + 0] = fmaf(v, q.x, acc[4 * c4 + 0]);
-                    acc[4 * c4 + 1] = fmaf(v, q.y, acc[4 * c4 + 1]);
-                    acc[4 * c4 + 2] = fmaf(v, q.z, acc[4 * c4 + 2]);
-                    acc[4 * c4 + 3] = fmaf(v, q.w, acc[4 * c4 + 3]);
-                }
+                const float4* wr = reinterpret_cast<const float4*>(s_w + (tap * cin + ci) * COUT + 8 * c8);
+                const float4 q0 = wr[0], q1 = wr[1];
+                acc[0] = fmaf(v, q0.x, acc[0]); acc[1] = fmaf(v, q0.y, acc[1]); acc[2] = fmaf(v, q0.z, acc[2]); acc[3] = fmaf(v, q0.w, acc[3]);
+                acc[4] = fmaf(v, q1.x, acc[4]); acc[5] = fmaf(v, q1.y, acc[5]); acc[6] = fmaf(v, q1.z, acc[6]); acc[7] = fmaf(v, q1.w, acc[7]);
             }
         }
-        __half* o = dst + pix * dst_ld;
+        float f[8];
 #pragma unroll
-        for (int c8 = 0; c8 < COUT / 8; ++c8) {
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { f[j] = fmaf(acc[8 * c8 + j], s_sc[8 * c8 + j], s_sh[8 * c8 + j]); if (relu) f[j] = fmaxf(f[j], 0.0f); }
-            if (dst_lo < 0) {                     // plain fp32 destination (train mode: the raw pre-BatchNorm tensor), row stride dst_ld floats
-                float4* of = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + pix * dst_ld + 8 * c8);
-                of[0] = make_float4(f[0], f[1], f[2], f[3]); of[1] = make_float4(f[4], f[5], f[6], f[7]);
-            } else {
-                store8(o, 8 * c8, dst_lo, fmt, f);
-            }
+        for (int j = 0; j < 8; ++j) { f[j] = fmaf(acc[j], s_sc[8 * c8 + j], s_sh[8 * c8 + j]); if (relu) f[j] = fmaxf(f[j], 0.0f); }
+        if (dst_lo < 0) {                     // plain fp32 destination (train mode: the raw pre-BatchNorm tensor), row stride dst_ld floats
+            float4* of = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + pix * dst_ld + 8 * c8);
+            of[0] = make_float4(f[0], f[1], f[2], f[3]); of[1] = make_float4(f[4], f[5], f[6], f[7]);
+        } else {
+            store8(dst + pix * dst_ld, 8 * c8, dst_lo, fmt, f);
         }
     }
 }
@@ -285,7 +282,7 @@ extern "C" int nbp_conv_first(const float* x, int n, int c_in, int h, int w, con
     if ((uintptr_t)dst & 15) return invalid("nbp_conv_first: dst must be 16-byte aligned");
     if (dst_lo >= 0 && (rc = check_fmt("nbp_conv_first", fmt, fmt == 2 ? dst_lo : 64))) return rc;
     const size_t smem = sizeof(float) * (size_t)(9 * c_in * 64 + 128);
-    conv_first_kernel<64><<<grid_for((size_t)n * h * w, 128), 128, smem, (cudaStream_t)stream>>>(x, n, c_in, h, w, weight, scale, shift,
+    conv_first_kernel<64><<<grid_for((size_t)n * h * w * 8, 256), 256, smem, (cudaStream_t)stream>>>(x, n, c_in, h, w, weight, scale, shift,
                                                                                                   (__half*)dst, dst_ld, dst_lo, relu, fmt);
     count_launch();
     return check_cuda(cudaGetLastError(), "nbp_conv_first launch");
