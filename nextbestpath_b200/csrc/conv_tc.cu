@@ -90,21 +90,36 @@ struct ConvKParams {
     __half* pool; int pool_ld, pool_lo_off;   // optional second output: the 2x2 max-pooled activation [n][h/2][w/2] (fused nn.MaxPool2d)
 };
 
-template <int BLOCK_N, int MODE, int HALO>     // MODE 0 fp16 | 1 fp16x2 | 2 fp16+e4m3; HALO = 0: plain stages; 2 | 3: halo stages carrying that many taps
+// MODE 0 fp16 | 1 fp16x2 | 2 fp16+e4m3 | 3 fp16+e4m3 with SPLIT stages; HALO = 0: plain stages; 2 | 3: halo stages carrying that many taps.
+// SPLIT (MODE 3, plain stages only): a 64-channel K slice travels as TWO pipeline stages -- {A_hi, W_hi} for the 4 fp16 UMMAs and
+// {A_p8, W_p8} for the 4 e4m3 UMMAs -- of half the size, so the ring holds 7 stages = 224 KB of operands in flight instead of
+// 3 x 64 = 192 KB.  These launches are bound by the TMA round trip (three 512-clock stages cannot cover it: measured 765 clocks per
+// slice, tensor pipe 65 % busy), i.e. by the bytes in flight.
+template <int BLOCK_N, int MODE, int HALO>
 struct ConvCfg {
     static constexpr bool PRECISE = MODE != 0;
-    static constexpr int PLANES = PRECISE ? 2 : 1;
+    static constexpr bool SPLIT = MODE == 3;
+    static_assert(!SPLIT || HALO == 0, "split stages exist for the plain path only");
+    static constexpr int PLANES = PRECISE ? 2 : 1;                        // planes per tensor / accumulators per tile
+    static constexpr int SPLANES = SPLIT ? 1 : PLANES;                    // planes carried by ONE pipeline stage
     static constexpr int A_PLANE = HALO ? A_HALO_BYTES : A_STAGE_BYTES;
-    static constexpr int A_BYTES = PLANES * A_PLANE;                      // A_hi [, A_lo]
-    static constexpr int B_ROWS = PLANES * BLOCK_N;                       // W_hi rows [, W_lo rows]
+    static constexpr int A_BYTES = SPLANES * A_PLANE;                     // A_hi [, A_lo]
+    static constexpr int NTILE_ROWS = PLANES * BLOCK_N;                   // rows of the packed weight matrix per n-tile: W_hi rows [, W_lo rows]
+    static constexpr int B_ROWS = SPLANES * BLOCK_N;                      // weight rows carried by one stage
     static constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 2;             // one tap x one 64-channel slice of the weights
     static constexpr int B_STAGE_BYTES = (HALO ? HALO : 1) * B_TILE_BYTES;
     static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES_RAW = (SMEM_LIMIT - SMEM_AUX - 1024) / STAGE_BYTES;
+    // SPLIT lays the auxiliary block (barriers, TMEM pointer, affine staging: < 3 KB) in FRONT of the ring and relies on the 1024-byte
+    // alignment of the dynamic shared-memory window (checked at run time) instead of reserving an alignment slack: 3 KB + 7 x 32 KB is
+    // exactly the 227 KB limit for 128-column tiles
+    static constexpr int AUX_FRONT = 3072;
+    static constexpr int STAGES_RAW = SPLIT ? (SMEM_LIMIT - AUX_FRONT) / STAGE_BYTES : (SMEM_LIMIT - SMEM_AUX - 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int ACC_COLS = PLANES * BLOCK_N;                     // acc_hi [, acc_lo] columns per buffer
     static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_AUX + 1024;   // +1024: manual 1024-B alignment
+    static constexpr int SMEM_BYTES = SPLIT ? AUX_FRONT + STAGES * STAGE_BYTES : STAGES * STAGE_BYTES + SMEM_AUX + 1024;   // +1024: manual 1024-B alignment
+    static_assert(!SPLIT || (2 * STAGES + 4) * 8 + 8 <= 512, "barriers overflow their slot");
+    static_assert(!SPLIT || 512 + 2 * 2 * BLOCK_N * 4 <= AUX_FRONT, "affine staging overflows the front block");
     static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
     static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
 };
@@ -116,13 +131,16 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     using Cfg = ConvCfg<BLOCK_N, MODE, HALO>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool PRECISE = MODE != 0;
-    constexpr bool FP8 = MODE == 2;
+    constexpr bool FP8 = MODE >= 2;
+    constexpr bool SPLIT = Cfg::SPLIT;
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = SPLIT ? smem_raw + Cfg::AUX_FRONT
+                          : reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    if (SPLIT && (smem_u32(smem_raw) & 1023u)) __trap();                // the swizzled operand tiles need 1024-byte aligned bases
     uint8_t* smem_a = smem;                                            // [STAGES][A_hi | A_lo]
     uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;                     // [STAGES][W_hi rows | W_lo rows]
-    uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES;
+    uint8_t* aux = SPLIT ? smem_raw : smem + STAGES * Cfg::STAGE_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);              // [STAGES]
     uint64_t* empty_bar = full_bar + STAGES;                            // [STAGES]
     uint64_t* tfull_bar = empty_bar + STAGES;                           // [2]
@@ -150,7 +168,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     const int tiles_per_parity = p.m_tiles * p.n_tiles;
     const int num_tiles = (p.up2x ? 4 : 1) * tiles_per_parity;
     const int kc_total = p.kc0 + p.kc1;
-    const int num_k = p.ngroups * kc_total;                              // stages per output tile (p.kchunk counts stages too)
+    const int num_k = p.ngroups * kc_total * (SPLIT ? 2 : 1);            // stages per output tile (p.kchunk counts stages too)
 
     if (warp == 0) {
         // ================================================================= TMA producer
@@ -165,7 +183,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                 const int ty = mt % p.tiles_y;
                 const int tb = mt / p.tiles_y;
                 const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tb * p.tn;
-                const int b_row0 = parity * p.b_rows_per_parity + n_tile * Cfg::B_ROWS;
+                const int b_row0 = parity * p.b_rows_per_parity + n_tile * Cfg::NTILE_ROWS;
                 for (int g = 0; g < p.ngroups; ++g) {
                     int dy = 0, dx = 0;
                     if (HALO) { dy = -1; dx = g - 1 + (p.up2x ? (parity & 1) : 0); }          // rows y0-1 .. y0+th of column offset dx
@@ -175,6 +193,19 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                         const bool first = kc < p.kc0;
                         const CUtensorMap* tm = first ? &tmA0 : &tmA1;
                         const int c = (first ? kc : kc - p.kc0) * BLOCK_K;
+                        if (SPLIT) {
+#pragma unroll
+                            for (int hf = 0; hf < 2; ++hf) {            // {A_hi, W_hi} then {A_p8, W_p8}: one stage each
+                                uint8_t* sa2 = smem_a + stage * Cfg::A_BYTES;
+                                uint8_t* sb2 = smem_b + stage * Cfg::B_STAGE_BYTES;
+                                mbar_wait(&empty_bar[stage], phase ^ 1);
+                                mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.a_tx + (uint32_t)Cfg::B_STAGE_BYTES);
+                                tma_load_4d(sa2, tm, &full_bar[stage], c + (hf ? (first ? p.lo0 : p.lo1) : 0), x0 + dx, y0 + dy, n0);
+                                tma_load_2d(sb2, &tmB, &full_bar[stage], (g * kc_total + kc) * BLOCK_K, b_row0 + hf * BLOCK_N);
+                                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            }
+                            continue;
+                        }
                         uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
                         uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
                         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -249,7 +280,18 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                     const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr);
                     const uint64_t alo = umma_desc_kmajor_sw128(a_addr + A_STAGE_BYTES);
                     const uint64_t blo = umma_desc_kmajor_sw128(b_addr + BLOCK_N * BLOCK_K * 2);     // the e4m3 weight rows (MODE 2)
-                    if (FP8) {
+                    if (SPLIT) {
+                        // even stages carry the fp16 operands (-> acc_hi), odd stages the e4m3 operands (-> acc_lo); chains start on an even stage
+                        if (((ks - ks0) & 1) == 0) {
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k)
+                                umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, (ks > ks0 || k > 0) ? 1u : 0u);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k)
+                                umma_f8(d_tmem + (uint32_t)BLOCK_N, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, (ks > ks0 + 1 || k > 0) ? 1u : 0u);
+                        }
+                    } else if (FP8) {
                         // hi product on the fp16 pipe, then both corrections as one K = 128 e4m3 reduction ([A_hi8 | A_lo8] . [W_lo8 ; W_hi8]);
                         // NBP_CONV_INTERLEAVE=0 issues the two kinds as two runs instead of alternating them (A/B switch; measured 1.3 % slower)
                         if (!p.interleave) {
@@ -614,21 +656,25 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     const int want = d->k_chunk > 0 ? d->k_chunk : (fp8 ? k8_env : kchunk_env);
     const bool halo = halo_env && precise && block_n <= 64 && (d->taps == 9 || d->up2x) && kp.tn == 1 && kp.tw >= 8 &&
                       (kp.th + 2) * kp.tw <= HALO_ROWS && !(want > 0 && want < 3);
-    const int planes_ = precise ? 2 : 1;
+    static int split_env = -1;
+    if (split_env < 0) { const char* e = getenv("NBP_CONV_SPLIT"); split_env = e ? atoi(e) : 1; }
+    const bool split = fp8 && !halo && split_env;                     // two half-size stages per K slice (ConvCfg, MODE 3)
+    const int planes_ = split ? 1 : precise ? 2 : 1;                  // planes carried by one pipeline stage
     kp.gtaps = halo ? (d->up2x ? 2 : 3) : 1;
     kp.ngroups = halo ? (d->up2x ? 2 : 3) : d->taps;
     kp.a_tx = planes_ * (halo ? kp.th + 2 : kp.th) * kp.tw * kp.tn * BLOCK_K * 2;
     kp.aoff_step = kp.tw * BLOCK_K * 2;
     {   // kp.kchunk = STAGES per accumulation chain (a halo stage carries gtaps K slices)
-        const int total = kp.ngroups * (kp.kc0 + kp.kc1);
-        int want_st = want <= 0 ? total : (want + kp.gtaps - 1) / kp.gtaps;
+        const int smult = split ? 2 : 1;                              // stages per K slice
+        const int total = kp.ngroups * (kp.kc0 + kp.kc1) * smult;
+        int want_st = want <= 0 ? total : (want + kp.gtaps - 1) / kp.gtaps * smult;
         kp.kchunk = !precise ? total : want_st;
         if (kp.kchunk > total) kp.kchunk = total;
         if (kp.kchunk < 1) kp.kchunk = 1;
         // A chain only slightly longer than the target (K = 9 slices of a 64-channel 3x3 layer vs 8) stays single: cutting it as
         // 8 + 1 makes the epilogue warps fold two chunks per tile for nothing (measured -3..-13 % on those layers); spreading
         // longer reductions evenly (18 as 6+6+6 instead of 8+8+2) was measured slower and is not done.
-        if (precise && want > 0 && total > kp.kchunk && total * kp.gtaps <= want + want / 4) kp.kchunk = total;
+        if (precise && want > 0 && total > kp.kchunk && total / smult * kp.gtaps <= want + want / 4) kp.kchunk = total;
     }
     kp.b_rows_per_parity = (precise ? 2 : 1) * d->c_out;
     kp.scale = d->scale; kp.shift = d->shift; kp.relu = d->relu;
@@ -653,7 +699,7 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     if (rc) return rc;
     // weights: fast [c_out][K]; precise [(c_out/block_n) tiles][W_hi rows ; W_lo rows][K]
     const int planes = precise ? 2 : 1;
-    rc = make_weight_map(&b, d->weight, d->taps * (d->c0 + d->c1), (d->up2x ? 4 : 1) * planes * d->c_out, planes * block_n);
+    rc = make_weight_map(&b, d->weight, d->taps * (d->c0 + d->c1), (d->up2x ? 4 : 1) * planes * d->c_out, (split ? 1 : planes) * block_n);
     if (rc) return rc;
 
     static int sms = 0;
@@ -665,6 +711,13 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
         if (rc) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (split) {
+        switch (block_n) {
+            case 128: return launch_conv<128, 3>(a0, a1, b, kp, sms, st);
+            case 64:  return launch_conv<64, 3>(a0, a1, b, kp, sms, st);
+            default:  return launch_conv<32, 3>(a0, a1, b, kp, sms, st);
+        }
+    }
     if (fp8) {
         switch (block_n) {
             case 128: return launch_conv<128, 2>(a0, a1, b, kp, sms, st);
