@@ -72,6 +72,8 @@ struct ConvKParams {
     int lo0, lo1;                       // element offset of the lo plane inside the tensor maps (PRECISE)
     float lo_scale;                     // acc = acc_hi + acc_lo * lo_scale (1/2048 for fp16x2, 1/(2048 s) for fp16+e4m3)
     int dst_fmt, pool_fmt;              // second-plane format written by the epilogue: 1 = fp16 lo*2048, 2 = e4m3 pair (MODE 2 consumers)
+    int cluster;                        // 1, or 2: CTA pairs (thread-block cluster) work on two m-tiles of the SAME n-tile in lock step and each
+                                        // loads half of every weight tile, multicast into both CTAs' shared memory (half the L2->SM weight bytes)
     int interleave;                     // MODE 2: 1 (default) = alternate the fp16 and e4m3 UMMAs per 16-element K step, 0 = two runs per stage
     unsigned long long* sat_count;      // optional: += number of (pixel, 32-channel group) stores in which an e4m3 value saturated
     int out_f32;                        // 1: the destination is plain fp32 NHWC (gradients), no fp16 planes
@@ -154,19 +156,28 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA0); prefetch_tmap(&tmA1); prefetch_tmap(&tmB);
     }
+    const int CL = p.cluster;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        // a slot is free again when the MMAs of EVERY CTA of the cluster have read it (peers multicast weight tiles into it)
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (uint32_t)CL); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                           // the peers' barriers exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    const int tiles_per_parity = p.m_tiles * p.n_tiles;
+    // work items: (parity, n-tile, group of CL consecutive m-tiles); the CTA of rank r in its cluster takes m-tile group * CL + r.  A rank
+    // beyond the last m-tile recomputes that tile as a ghost (it must keep the cluster's barrier handshakes going) and stores nothing.
+    const int m_groups = (p.m_tiles + CL - 1) / CL;
+    const int tiles_per_parity = m_groups * p.n_tiles;
     const int num_tiles = (p.up2x ? 4 : 1) * tiles_per_parity;
+    const int tile0 = blockIdx.x / CL, tile_step = gridDim.x / CL;
     const int kc_total = p.kc0 + p.kc1;
     const int num_k = p.ngroups * kc_total * (SPLIT ? 2 : 1);            // stages per output tile (p.kchunk counts stages too)
 
@@ -174,11 +185,20 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         // ================================================================= TMA producer
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            // one weight tile of `rows` rows: the whole box, or this CTA's 1/CL of the rows multicast to every CTA of the cluster
+            auto load_b = [&](uint8_t* dst, uint64_t* bar, int k_elem, int row, int rows) {
+                if (CL > 1) {
+                    const int part = rows / CL;
+                    tma_load_2d_mc(dst + (size_t)crank * part * (BLOCK_K * 2), &tmB, bar, k_elem, row + (int)crank * part, cmask);
+                } else {
+                    tma_load_2d(dst, &tmB, bar, k_elem, row);
+                }
+            };
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 const int parity = tile / tiles_per_parity;              // 0 unless up2x: (py, px) = (parity >> 1, parity & 1)
                 const int tpl = tile - parity * tiles_per_parity;
                 const int n_tile = tpl % p.n_tiles;
-                int mt = tpl / p.n_tiles;
+                int mt = min((tpl / p.n_tiles) * CL + (int)crank, p.m_tiles - 1);
                 const int tx = mt % p.tiles_x; mt /= p.tiles_x;
                 const int ty = mt % p.tiles_y;
                 const int tb = mt / p.tiles_y;
@@ -201,7 +221,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                                 mbar_wait(&empty_bar[stage], phase ^ 1);
                                 mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.a_tx + (uint32_t)Cfg::B_STAGE_BYTES);
                                 tma_load_4d(sa2, tm, &full_bar[stage], c + (hf ? (first ? p.lo0 : p.lo1) : 0), x0 + dx, y0 + dy, n0);
-                                tma_load_2d(sb2, &tmB, &full_bar[stage], (g * kc_total + kc) * BLOCK_K, b_row0 + hf * BLOCK_N);
+                                load_b(sb2, &full_bar[stage], (g * kc_total + kc) * BLOCK_K, b_row0 + hf * BLOCK_N, Cfg::B_ROWS);
                                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
                             }
                             continue;
@@ -216,10 +236,10 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 #pragma unroll
                             for (int j = 0; j < HALO; ++j) {                                   // taps (dy = j-1 | j-1+py) of this column
                                 const int tap = p.up2x ? j * 2 + g : j * 3 + g;
-                                tma_load_2d(sb + j * Cfg::B_TILE_BYTES, &tmB, &full_bar[stage], (tap * kc_total + kc) * BLOCK_K, b_row0);
+                                load_b(sb + j * Cfg::B_TILE_BYTES, &full_bar[stage], (tap * kc_total + kc) * BLOCK_K, b_row0, Cfg::B_ROWS);
                             }
                         } else {
-                            tma_load_2d(sb, &tmB, &full_bar[stage], (g * kc_total + kc) * BLOCK_K, b_row0);
+                            load_b(sb, &full_bar[stage], (g * kc_total + kc) * BLOCK_K, b_row0, Cfg::B_ROWS);
                         }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -233,7 +253,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             constexpr uint32_t idesc_lo = umma_idesc_f16(BLOCK_M, BLOCK_N);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
               for (int ks0 = 0; ks0 < num_k; ks0 += p.kchunk) {
                 const int ks1 = min(num_k, ks0 + p.kchunk);
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -320,7 +340,8 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                     }
                     }
                     }
-                    umma_commit(&empty_bar[stage]);           // frees the smem slot once these MMAs have read it
+                    // frees the smem slot once these MMAs have read it -- in every CTA of the cluster, whose producers write into it
+                    if (CL > 1) umma_commit_mc(&empty_bar[stage], cmask); else umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull_bar[acc]);                  // (partial) accumulator complete -> epilogue
@@ -336,17 +357,19 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         int acc = 0; uint32_t acc_phase = 0;
         int tsel = 0;
         const int n_chunks = (num_k + p.kchunk - 1) / p.kchunk;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             const int parity = tile / tiles_per_parity;
             const int tpl = tile - parity * tiles_per_parity;
             const int n_tile = tpl % p.n_tiles;
-            int mt = tpl / p.n_tiles;
+            int mt = (tpl / p.n_tiles) * CL + (int)crank;
+            const bool ghost = mt >= p.m_tiles;
+            mt = min(mt, p.m_tiles - 1);
             const int tx = mt % p.tiles_x; mt /= p.tiles_x;
             const int ty = mt % p.tiles_y;
             const int tb = mt / p.tiles_y;
             const int wi = m % p.tw, hi = (m / p.tw) % p.th, ni = m / (p.tw * p.th);
             const int x = tx * p.tw + wi, y = ty * p.th + hi, nn = tb * p.tn + ni;
-            const bool valid = x < p.w && y < p.h && nn < p.n;
+            const bool valid = x < p.w && y < p.h && nn < p.n && !ghost;
             // destination pixel: identity, or (2y+py, 2x+px) of the 2h x 2w image for the fused upsample
             const int oh = p.up2x ? 2 * p.h : p.h, ow = p.up2x ? 2 * p.w : p.w;
             const int oy = p.up2x ? 2 * y + (parity >> 1) : y, ox = p.up2x ? 2 * x + (parity & 1) : x;
@@ -503,6 +526,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                           // no CTA leaves while a peer may still multicast into it or arrive on its barriers
     if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
@@ -570,18 +594,41 @@ template <int BLOCK_N, int MODE, int HALO = 0>
 static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvKParams& kp, int sms, cudaStream_t st) {
     using Cfg = ConvCfg<BLOCK_N, MODE, HALO>;
     static bool attr_set = false;
+    static int max_clusters2 = 0;          // co-resident 2-CTA clusters of this instantiation (0 = not queried yet)
+    auto kern = conv_gemm_f16<BLOCK_N, MODE, HALO>;
     if (!attr_set) {
-        int rc = check_cuda(cudaFuncSetAttribute(conv_gemm_f16<BLOCK_N, MODE, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES),
+        int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES),
                             "cudaFuncSetAttribute(conv_gemm_f16)");
         if (rc) return rc;
         attr_set = true;
     }
-    const int tiles = kp.m_tiles * kp.n_tiles * (kp.up2x ? 4 : 1);
-    const int grid = tiles < sms ? tiles : sms;
+    const int CL = kp.cluster;
+    const int work = ((kp.m_tiles + CL - 1) / CL) * kp.n_tiles * (kp.up2x ? 4 : 1);       // work items of one cluster (or CTA)
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(CONV_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    int slots = sms;
+    if (CL > 1) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (!max_clusters2) {
+            cfg.gridDim = dim3((unsigned)(sms / CL * CL));
+            int n = 0;
+            int rc = check_cuda(cudaOccupancyMaxActiveClusters(&n, kern, &cfg), "cudaOccupancyMaxActiveClusters(conv_gemm_f16)");
+            if (rc) return rc;
+            if (n < 1) { set_error("conv_gemm_f16: no 2-CTA cluster fits on this device"); return NBP_ERR_UNSUPPORTED; }
+            max_clusters2 = n;
+        }
+        slots = max_clusters2;
+    }
+    cfg.gridDim = dim3((unsigned)((work < slots ? work : slots) * CL));
     const bool prof = g_prof.enabled && g_prof.used + 2 <= g_prof.ev.size();
     if (g_prof.enabled && !prof) ++g_prof.dropped;
     if (prof) cudaEventRecord(g_prof.ev[g_prof.used], st);
-    conv_gemm_f16<BLOCK_N, MODE, HALO><<<grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(a0, a1, b, kp);
+    int rc = check_cuda(cudaLaunchKernelEx(&cfg, kern, a0, a1, b, kp), "conv_gemm_f16 launch");
     if (prof) {
         cudaEventRecord(g_prof.ev[g_prof.used + 1], st);
         g_prof.used += 2;
@@ -590,7 +637,7 @@ static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
         g_prof.flops += 2.0 * pix * (double)(kp.n_tiles * BLOCK_N) * ktaps * (double)((kp.kc0 + kp.kc1) * BLOCK_K);
     }
     count_launch();
-    return check_cuda(cudaGetLastError(), "conv_gemm_f16 launch");
+    return rc;
 }
 
 }  // namespace nbp
@@ -656,7 +703,9 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     const int want = d->k_chunk > 0 ? d->k_chunk : (fp8 ? k8_env : kchunk_env);
     const bool halo = halo_env && precise && block_n <= 64 && (d->taps == 9 || d->up2x) && kp.tn == 1 && kp.tw >= 8 &&
                       (kp.th + 2) * kp.tw <= HALO_ROWS && !(want > 0 && want < 3);
-    static int split_env = -1;
+    static int split_env = -1, cluster_env = -1;
+    if (cluster_env < 0) { const char* e = getenv("NBP_CONV_CLUSTER"); cluster_env = e ? atoi(e) : 2; }
+    kp.cluster = (cluster_env >= 2 && kp.m_tiles >= 2) ? 2 : 1;
     if (split_env < 0) { const char* e = getenv("NBP_CONV_SPLIT"); split_env = e ? atoi(e) : 1; }
     const bool split = fp8 && !halo && split_env;                     // two half-size stages per K slice (ConvCfg, MODE 3)
     const int planes_ = split ? 1 : precise ? 2 : 1;                  // planes carried by one pipeline stage
@@ -699,7 +748,7 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     if (rc) return rc;
     // weights: fast [c_out][K]; precise [(c_out/block_n) tiles][W_hi rows ; W_lo rows][K]
     const int planes = precise ? 2 : 1;
-    rc = make_weight_map(&b, d->weight, d->taps * (d->c0 + d->c1), (d->up2x ? 4 : 1) * planes * d->c_out, (split ? 1 : planes) * block_n);
+    rc = make_weight_map(&b, d->weight, d->taps * (d->c0 + d->c1), (d->up2x ? 4 : 1) * planes * d->c_out, (split ? 1 : planes) * block_n / kp.cluster);
     if (rc) return rc;
 
     static int sms = 0;
