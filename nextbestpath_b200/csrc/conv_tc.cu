@@ -97,17 +97,21 @@ struct ConvKParams {
 // {A_p8, W_p8} for the 4 e4m3 UMMAs -- of half the size, so the ring holds 7 stages = 224 KB of operands in flight instead of
 // 3 x 64 = 192 KB.  These launches are bound by the TMA round trip (three 512-clock stages cannot cover it: measured 765 clocks per
 // slice, tensor pipe 65 % busy), i.e. by the bytes in flight.
-template <int BLOCK_N, int MODE, int HALO>
+// PAIR: two CTAs of a cluster form one tcgen05 cta_group::2 unit: an MMA of M = 256 (two adjacent m-tiles) x BLOCK_N whose B operand is
+// split between them -- each CTA stages its own 128 pixel rows of A and only HALF of the weight rows, so the bytes an SM takes in per flop
+// fall by a quarter (these launches run at the ~85-90 B/clk an SM ingests from L2: DESIGN.md 4.1).  The even CTA issues every MMA.
+template <int BLOCK_N, int MODE, int HALO, bool PAIR = false>
 struct ConvCfg {
     static constexpr bool PRECISE = MODE != 0;
     static constexpr bool SPLIT = MODE == 3;
     static_assert(!SPLIT || HALO == 0, "split stages exist for the plain path only");
+    static_assert(!PAIR || (HALO == 0 && SPLIT), "CTA pairs are built for the split fp16+e4m3 path");
     static constexpr int PLANES = PRECISE ? 2 : 1;                        // planes per tensor / accumulators per tile
     static constexpr int SPLANES = SPLIT ? 1 : PLANES;                    // planes carried by ONE pipeline stage
     static constexpr int A_PLANE = HALO ? A_HALO_BYTES : A_STAGE_BYTES;
     static constexpr int A_BYTES = SPLANES * A_PLANE;                     // A_hi [, A_lo]
     static constexpr int NTILE_ROWS = PLANES * BLOCK_N;                   // rows of the packed weight matrix per n-tile: W_hi rows [, W_lo rows]
-    static constexpr int B_ROWS = SPLANES * BLOCK_N;                      // weight rows carried by one stage
+    static constexpr int B_ROWS = SPLANES * BLOCK_N / (PAIR ? 2 : 1);     // weight rows carried by one stage of one CTA
     static constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 2;             // one tap x one 64-channel slice of the weights
     static constexpr int B_STAGE_BYTES = (HALO ? HALO : 1) * B_TILE_BYTES;
     static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
@@ -116,7 +120,7 @@ struct ConvCfg {
     // exactly the 227 KB limit for 128-column tiles
     static constexpr int AUX_FRONT = 3072;
     static constexpr int STAGES_RAW = SPLIT ? (SMEM_LIMIT - AUX_FRONT) / STAGE_BYTES : (SMEM_LIMIT - SMEM_AUX - 1024) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int STAGES = STAGES_RAW > (PAIR ? 9 : 8) ? (PAIR ? 9 : 8) : STAGES_RAW;
     static constexpr int ACC_COLS = PLANES * BLOCK_N;                     // acc_hi [, acc_lo] columns per buffer
     static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
     static constexpr int SMEM_BYTES = SPLIT ? AUX_FRONT + STAGES * STAGE_BYTES : STAGES * STAGE_BYTES + SMEM_AUX + 1024;   // +1024: manual 1024-B alignment
@@ -126,11 +130,11 @@ struct ConvCfg {
     static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
 };
 
-template <int BLOCK_N, int MODE, int HALO>
+template <int BLOCK_N, int MODE, int HALO, bool PAIR = false>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
               const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
-    using Cfg = ConvCfg<BLOCK_N, MODE, HALO>;
+    using Cfg = ConvCfg<BLOCK_N, MODE, HALO, PAIR>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool PRECISE = MODE != 0;
     constexpr bool FP8 = MODE >= 2;
@@ -161,11 +165,12 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
     if (warp == 1 && lane == 0) {
         // a slot is free again when the MMAs of EVERY CTA of the cluster have read it (peers multicast weight tiles into it)
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (uint32_t)CL); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+        // PAIR: the even CTA's full barrier collects one arrival per CTA (+ both CTAs' bytes), its MMAs release the slot in both CTAs
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], PAIR ? 2u : 1u); mbar_init(&empty_bar[s], PAIR ? 1u : (uint32_t)CL); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], PAIR ? 8 : 4); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    if (warp == 2) { if (PAIR) tmem_alloc_pair(tmem_ptr, Cfg::TMEM_COLS); else tmem_alloc(tmem_ptr, Cfg::TMEM_COLS); }
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();                           // the peers' barriers exist before anything is multicast at them
@@ -187,7 +192,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             int stage = 0; uint32_t phase = 0;
             // one weight tile of `rows` rows: the whole box, or this CTA's 1/CL of the rows multicast to every CTA of the cluster
             auto load_b = [&](uint8_t* dst, uint64_t* bar, int k_elem, int row, int rows) {
-                if (CL > 1) {
+                if (CL > 1 && !PAIR) {
                     const int part = rows / CL;
                     tma_load_2d_mc(dst + (size_t)crank * part * (BLOCK_K * 2), &tmB, bar, k_elem, row + (int)crank * part, cmask);
                 } else {
@@ -219,6 +224,16 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                                 uint8_t* sa2 = smem_a + stage * Cfg::A_BYTES;
                                 uint8_t* sb2 = smem_b + stage * Cfg::B_STAGE_BYTES;
                                 mbar_wait(&empty_bar[stage], phase ^ 1);
+                                if (PAIR) {
+                                    // both CTAs' boxes are credited to the even CTA's barrier, which expects the bytes of the pair
+                                    if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * ((uint32_t)p.a_tx + (uint32_t)Cfg::B_STAGE_BYTES));
+                                    else mbar_arrive_remote(&full_bar[stage], 0u);
+                                    tma_load_4d_pair(sa2, tm, &full_bar[stage], c + (hf ? (first ? p.lo0 : p.lo1) : 0), x0 + dx, y0 + dy, n0);
+                                    tma_load_2d_pair(sb2, &tmB, &full_bar[stage], (g * kc_total + kc) * BLOCK_K,
+                                                     b_row0 + hf * BLOCK_N + (int)crank * Cfg::B_ROWS);
+                                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                                    continue;
+                                }
                                 mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.a_tx + (uint32_t)Cfg::B_STAGE_BYTES);
                                 tma_load_4d(sa2, tm, &full_bar[stage], c + (hf ? (first ? p.lo0 : p.lo1) : 0), x0 + dx, y0 + dy, n0);
                                 load_b(sb2, &full_bar[stage], (g * kc_total + kc) * BLOCK_K, b_row0 + hf * BLOCK_N, Cfg::B_ROWS);
@@ -246,11 +261,11 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================================================================= MMA issuer
+    } else if (warp == 1 && !(PAIR && crank != 0)) {
+        // ================================================================= MMA issuer (PAIR: the even CTA issues for both)
         if (elect_one()) {
             constexpr uint32_t idesc_main = umma_idesc_f16(BLOCK_M, Cfg::B_ROWS);   // N = BLOCK_N, or 2*BLOCK_N over [W_hi ; W_lo]
-            constexpr uint32_t idesc_lo = umma_idesc_f16(BLOCK_M, BLOCK_N);
+            constexpr uint32_t idesc_lo = umma_idesc_f16(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -304,12 +319,16 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                         // even stages carry the fp16 operands (-> acc_hi), odd stages the e4m3 operands (-> acc_lo); chains start on an even stage
                         if (((ks - ks0) & 1) == 0) {
 #pragma unroll
-                            for (int k = 0; k < BLOCK_K / 16; ++k)
-                                umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, (ks > ks0 || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < BLOCK_K / 16; ++k) {
+                                if (PAIR) umma_f16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, (ks > ks0 || k > 0) ? 1u : 0u);
+                                else umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, (ks > ks0 || k > 0) ? 1u : 0u);
+                            }
                         } else {
 #pragma unroll
-                            for (int k = 0; k < BLOCK_K / 16; ++k)
-                                umma_f8(d_tmem + (uint32_t)BLOCK_N, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, (ks > ks0 + 1 || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < BLOCK_K / 16; ++k) {
+                                if (PAIR) umma_f8_pair(d_tmem + (uint32_t)BLOCK_N, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, (ks > ks0 + 1 || k > 0) ? 1u : 0u);
+                                else umma_f8(d_tmem + (uint32_t)BLOCK_N, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, (ks > ks0 + 1 || k > 0) ? 1u : 0u);
+                            }
                         }
                     } else if (FP8) {
                         // hi product on the fp16 pipe, then both corrections as one K = 128 e4m3 reduction ([A_hi8 | A_lo8] . [W_lo8 ; W_hi8]);
@@ -341,10 +360,11 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                     }
                     }
                     // frees the smem slot once these MMAs have read it -- in every CTA of the cluster, whose producers write into it
-                    if (CL > 1) umma_commit_mc(&empty_bar[stage], cmask); else umma_commit(&empty_bar[stage]);
+                    if (PAIR) umma_commit_pair(&empty_bar[stage]);
+                    else if (CL > 1) umma_commit_mc(&empty_bar[stage], cmask); else umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);                  // (partial) accumulator complete -> epilogue
+                if (PAIR) umma_commit_pair(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);   // (partial) accumulator complete -> epilogue(s)
                 acc ^= 1; if (acc == 0) acc_phase ^= 1;
               }
             }
@@ -484,7 +504,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             auto release = [&]() {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0) { if (PAIR) mbar_arrive_remote(&tempty_bar[acc], 0u); else mbar_arrive(&tempty_bar[acc]); }
                 acc ^= 1; if (acc == 0) acc_phase ^= 1;
             };
 
@@ -527,7 +547,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();                           // no CTA leaves while a peer may still multicast into it or arrive on its barriers
-    if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (warp == 2) { if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -590,12 +610,12 @@ static ConvProfile g_prof;
 static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 static int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
 
-template <int BLOCK_N, int MODE, int HALO = 0>
+template <int BLOCK_N, int MODE, int HALO = 0, bool PAIR = false>
 static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvKParams& kp, int sms, cudaStream_t st) {
-    using Cfg = ConvCfg<BLOCK_N, MODE, HALO>;
+    using Cfg = ConvCfg<BLOCK_N, MODE, HALO, PAIR>;
     static bool attr_set = false;
     static int max_clusters2 = 0;          // co-resident 2-CTA clusters of this instantiation (0 = not queried yet)
-    auto kern = conv_gemm_f16<BLOCK_N, MODE, HALO>;
+    auto kern = conv_gemm_f16<BLOCK_N, MODE, HALO, PAIR>;
     if (!attr_set) {
         int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES),
                             "cudaFuncSetAttribute(conv_gemm_f16)");
@@ -708,6 +728,10 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     kp.cluster = (cluster_env >= 2 && kp.m_tiles >= 2) ? 2 : 1;
     if (split_env < 0) { const char* e = getenv("NBP_CONV_SPLIT"); split_env = e ? atoi(e) : 1; }
     const bool split = fp8 && !halo && split_env;                     // two half-size stages per K slice (ConvCfg, MODE 3)
+    static int pair_env = -1;
+    if (pair_env < 0) { const char* e = getenv("NBP_CONV_PAIR"); pair_env = e ? atoi(e) : 1; }
+    const bool pair = split && block_n == 128 && kp.m_tiles >= 2 && pair_env;      // cta_group::2 tiles (ConvCfg, PAIR)
+    if (pair) kp.cluster = 2;
     const int planes_ = split ? 1 : precise ? 2 : 1;                  // planes carried by one pipeline stage
     kp.gtaps = halo ? (d->up2x ? 2 : 3) : 1;
     kp.ngroups = halo ? (d->up2x ? 2 : 3) : d->taps;
@@ -760,6 +784,7 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
         if (rc) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (pair) return launch_conv<128, 3, 0, true>(a0, a1, b, kp, sms, st);
     if (split) {
         switch (block_n) {
             case 128: return launch_conv<128, 3>(a0, a1, b, kp, sms, st);
