@@ -105,7 +105,7 @@ struct ConvCfg {
     static constexpr bool PRECISE = MODE != 0;
     static constexpr bool SPLIT = MODE == 3;
     static_assert(!SPLIT || HALO == 0, "split stages exist for the plain path only");
-    static_assert(!PAIR || (HALO == 0 && SPLIT), "CTA pairs are built for the split fp16+e4m3 path");
+    static_assert(!PAIR || (HALO == 0 && (MODE == 1 || MODE == 3)), "CTA pairs are built for the plain fp16x2 and split fp16+e4m3 paths");
     static constexpr int PLANES = PRECISE ? 2 : 1;                        // planes per tensor / accumulators per tile
     static constexpr int SPLANES = SPLIT ? 1 : PLANES;                    // planes carried by ONE pipeline stage
     static constexpr int A_PLANE = HALO ? A_HALO_BYTES : A_STAGE_BYTES;
@@ -244,6 +244,17 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                         uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
                         uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
                         mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (PAIR) {        // fp16x2 pair: A_hi, A_lo of this CTA's pixels + its half of the W_hi rows and of the W_lo rows
+                            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * ((uint32_t)p.a_tx + (uint32_t)Cfg::B_STAGE_BYTES));
+                            else mbar_arrive_remote(&full_bar[stage], 0u);
+                            const int lo = first ? p.lo0 : p.lo1, kel = (g * kc_total + kc) * BLOCK_K;
+                            tma_load_4d_pair(sa, tm, &full_bar[stage], c, x0 + dx, y0 + dy, n0);
+                            tma_load_4d_pair(sa + Cfg::A_PLANE, tm, &full_bar[stage], c + lo, x0 + dx, y0 + dy, n0);
+                            tma_load_2d_pair(sb, &tmB, &full_bar[stage], kel, b_row0 + (int)crank * (BLOCK_N / 2));
+                            tma_load_2d_pair(sb + (BLOCK_N / 2) * BLOCK_K * 2, &tmB, &full_bar[stage], kel, b_row0 + BLOCK_N + (int)crank * (BLOCK_N / 2));
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
                         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.a_tx + (uint32_t)Cfg::B_STAGE_BYTES);
                         tma_load_4d(sa, tm, &full_bar[stage], c, x0 + dx, y0 + dy, n0);
                         if (PRECISE) tma_load_4d(sa + Cfg::A_PLANE, tm, &full_bar[stage], c + (first ? p.lo0 : p.lo1), x0 + dx, y0 + dy, n0);
@@ -315,7 +326,18 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                     const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr);
                     const uint64_t alo = umma_desc_kmajor_sw128(a_addr + A_STAGE_BYTES);
                     const uint64_t blo = umma_desc_kmajor_sw128(b_addr + BLOCK_N * BLOCK_K * 2);     // the e4m3 weight rows (MODE 2)
-                    if (SPLIT) {
+                    if (PAIR && !SPLIT) {
+                        // fp16x2 over a CTA pair: three M = 256 x N = BLOCK_N products per 16-element K step; this CTA's B tile holds its half
+                        // of the W_hi rows followed by its half of the W_lo rows
+                        const uint64_t bhi = bdesc, blo2 = umma_desc_kmajor_sw128(b_addr + (BLOCK_N / 2) * BLOCK_K * 2);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / 16; ++k) {
+                            const uint32_t accum = (ks > ks0 || k > 0) ? 1u : 0u;
+                            umma_f16_pair(d_tmem, adesc + (uint64_t)(2 * k), bhi + (uint64_t)(2 * k), idesc_lo, accum);
+                            umma_f16_pair(d_tmem + (uint32_t)BLOCK_N, adesc + (uint64_t)(2 * k), blo2 + (uint64_t)(2 * k), idesc_lo, accum);
+                            umma_f16_pair(d_tmem + (uint32_t)BLOCK_N, alo + (uint64_t)(2 * k), bhi + (uint64_t)(2 * k), idesc_lo, 1u);
+                        }
+                    } else if (SPLIT) {
                         // even stages carry the fp16 operands (-> acc_hi), odd stages the e4m3 operands (-> acc_lo); chains start on an even stage
                         if (((ks - ks0) & 1) == 0) {
 #pragma unroll
@@ -730,7 +752,8 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     const bool split = fp8 && !halo && split_env;                     // two half-size stages per K slice (ConvCfg, MODE 3)
     static int pair_env = -1;
     if (pair_env < 0) { const char* e = getenv("NBP_CONV_PAIR"); pair_env = e ? atoi(e) : 1; }
-    const bool pair = split && block_n == 128 && kp.m_tiles >= 2 && pair_env;      // cta_group::2 tiles (ConvCfg, PAIR)
+    // cta_group::2 tiles (ConvCfg, PAIR): the 128-column plain launches of the fp16+e4m3 (split) and fp16x2 modes
+    const bool pair = block_n == 128 && !halo && (split || d->precise == 1) && kp.m_tiles >= 2 && pair_env;
     if (pair) kp.cluster = 2;
     const int planes_ = split ? 1 : precise ? 2 : 1;                  // planes carried by one pipeline stage
     kp.gtaps = halo ? (d->up2x ? 2 : 3) : 1;
@@ -772,7 +795,7 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     if (rc) return rc;
     // weights: fast [c_out][K]; precise [(c_out/block_n) tiles][W_hi rows ; W_lo rows][K]
     const int planes = precise ? 2 : 1;
-    rc = make_weight_map(&b, d->weight, d->taps * (d->c0 + d->c1), (d->up2x ? 4 : 1) * planes * d->c_out, (split ? 1 : planes) * block_n / kp.cluster);
+    rc = make_weight_map(&b, d->weight, d->taps * (d->c0 + d->c1), (d->up2x ? 4 : 1) * planes * d->c_out, pair ? block_n / 2 : (split ? 1 : planes) * block_n / kp.cluster);
     if (rc) return rc;
 
     static int sms = 0;
@@ -784,7 +807,7 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
         if (rc) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (pair) return launch_conv<128, 3, 0, true>(a0, a1, b, kp, sms, st);
+    if (pair) return split ? launch_conv<128, 3, 0, true>(a0, a1, b, kp, sms, st) : launch_conv<128, 1, 0, true>(a0, a1, b, kp, sms, st);
     if (split) {
         switch (block_n) {
             case 128: return launch_conv<128, 3>(a0, a1, b, kp, sms, st);
