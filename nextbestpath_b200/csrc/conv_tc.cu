@@ -105,7 +105,8 @@ struct ConvCfg {
     static constexpr bool PRECISE = MODE != 0;
     static constexpr bool SPLIT = MODE == 3;
     static_assert(!SPLIT || HALO == 0, "split stages exist for the plain path only");
-    static_assert(!PAIR || (HALO == 0 && (MODE == 1 || MODE == 3)), "CTA pairs are built for the plain fp16x2 and split fp16+e4m3 paths");
+    static_assert(!PAIR || (HALO == 0 && (MODE == 1 || MODE == 3)) || (HALO != 0 && (MODE == 1 || MODE == 2)),
+                  "CTA pairs: plain fp16x2 / split fp16+e4m3 launches and the halo launches of both parity modes");
     static constexpr int PLANES = PRECISE ? 2 : 1;                        // planes per tensor / accumulators per tile
     static constexpr int SPLANES = SPLIT ? 1 : PLANES;                    // planes carried by ONE pipeline stage
     static constexpr int A_PLANE = HALO ? A_HALO_BYTES : A_STAGE_BYTES;
@@ -247,11 +248,17 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                         if (PAIR) {        // fp16x2 pair: A_hi, A_lo of this CTA's pixels + its half of the W_hi rows and of the W_lo rows
                             if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * ((uint32_t)p.a_tx + (uint32_t)Cfg::B_STAGE_BYTES));
                             else mbar_arrive_remote(&full_bar[stage], 0u);
-                            const int lo = first ? p.lo0 : p.lo1, kel = (g * kc_total + kc) * BLOCK_K;
+                            const int lo = first ? p.lo0 : p.lo1;
                             tma_load_4d_pair(sa, tm, &full_bar[stage], c, x0 + dx, y0 + dy, n0);
                             tma_load_4d_pair(sa + Cfg::A_PLANE, tm, &full_bar[stage], c + lo, x0 + dx, y0 + dy, n0);
-                            tma_load_2d_pair(sb, &tmB, &full_bar[stage], kel, b_row0 + (int)crank * (BLOCK_N / 2));
-                            tma_load_2d_pair(sb + (BLOCK_N / 2) * BLOCK_K * 2, &tmB, &full_bar[stage], kel, b_row0 + BLOCK_N + (int)crank * (BLOCK_N / 2));
+#pragma unroll
+                            for (int j = 0; j < (HALO ? HALO : 1); ++j) {            // per tap tile: [half of the hi rows | half of the second-plane rows]
+                                const int tap = !HALO ? g : p.up2x ? j * 2 + g : j * 3 + g;
+                                const int kel = (tap * kc_total + kc) * BLOCK_K;
+                                uint8_t* dstb = sb + j * Cfg::B_TILE_BYTES;
+                                tma_load_2d_pair(dstb, &tmB, &full_bar[stage], kel, b_row0 + (int)crank * (BLOCK_N / 2));
+                                tma_load_2d_pair(dstb + (BLOCK_N / 2) * BLOCK_K * 2, &tmB, &full_bar[stage], kel, b_row0 + BLOCK_N + (int)crank * (BLOCK_N / 2));
+                            }
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                             continue;
                         }
@@ -300,7 +307,21 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                             const uint64_t alo = umma_desc_kmajor_sw128(a_addr + (uint32_t)((row0 + j) * p.aoff_step) + Cfg::A_PLANE);
                             const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr + (uint32_t)(j * Cfg::B_TILE_BYTES));
                             const uint64_t blo = umma_desc_kmajor_sw128(b_addr + (uint32_t)(j * Cfg::B_TILE_BYTES + BLOCK_N * BLOCK_K * 2));
-                            if (FP8 && !p.interleave) {
+                            if (PAIR) {
+                                // this CTA's tap tile = [half of the W_hi rows | half of the second-plane rows]; three (fp16x2) or two (fp16 + e4m3) pair MMAs
+                                const uint64_t b2 = umma_desc_kmajor_sw128(b_addr + (uint32_t)(j * Cfg::B_TILE_BYTES + (BLOCK_N / 2) * BLOCK_K * 2));
+#pragma unroll
+                                for (int k = 0; k < BLOCK_K / 16; ++k) {
+                                    const uint32_t accum = (ks > ks0 || j > 0 || k > 0) ? 1u : 0u;
+                                    umma_f16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, accum);
+                                    if (FP8) {
+                                        umma_f8_pair(d_tmem + (uint32_t)BLOCK_N, alo + (uint64_t)(2 * k), b2 + (uint64_t)(2 * k), idesc_lo, accum);
+                                    } else {
+                                        umma_f16_pair(d_tmem + (uint32_t)BLOCK_N, adesc + (uint64_t)(2 * k), b2 + (uint64_t)(2 * k), idesc_lo, accum);
+                                        umma_f16_pair(d_tmem + (uint32_t)BLOCK_N, alo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, 1u);
+                                    }
+                                }
+                            } else if (FP8 && !p.interleave) {
 #pragma unroll
                                 for (int k = 0; k < BLOCK_K / 16; ++k)
                                     umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_lo, (ks > ks0 || j > 0 || k > 0) ? 1u : 0u);
@@ -753,7 +774,8 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     static int pair_env = -1;
     if (pair_env < 0) { const char* e = getenv("NBP_CONV_PAIR"); pair_env = e ? atoi(e) : 1; }
     // cta_group::2 tiles (ConvCfg, PAIR): the 128-column plain launches of the fp16+e4m3 (split) and fp16x2 modes
-    const bool pair = block_n == 128 && !halo && (split || d->precise == 1) && kp.m_tiles >= 2 && pair_env;
+    const bool pair = pair_env && kp.m_tiles >= 2 &&
+                      ((block_n == 128 && !halo && (split || d->precise == 1)) || (block_n == 64 && halo && precise));
     if (pair) kp.cluster = 2;
     const int planes_ = split ? 1 : precise ? 2 : 1;                  // planes carried by one pipeline stage
     kp.gtaps = halo ? (d->up2x ? 2 : 3) : 1;
@@ -807,6 +829,10 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
         if (rc) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (pair && halo) {
+        if (fp8) return d->up2x ? launch_conv<64, 2, 2, true>(a0, a1, b, kp, sms, st) : launch_conv<64, 2, 3, true>(a0, a1, b, kp, sms, st);
+        return d->up2x ? launch_conv<64, 1, 2, true>(a0, a1, b, kp, sms, st) : launch_conv<64, 1, 3, true>(a0, a1, b, kp, sms, st);
+    }
     if (pair) return split ? launch_conv<128, 3, 0, true>(a0, a1, b, kp, sms, st) : launch_conv<128, 1, 0, true>(a0, a1, b, kp, sms, st);
     if (split) {
         switch (block_n) {
