@@ -80,54 +80,83 @@ __device__ __forceinline__ void store8(__half* pix, int ch, int lo, int fmt, con
 }
 
 // ------------------------------------------------------------------------------------------------ conv_first
-// 8 lanes per pixel, 8 output channels per lane: the 8 lanes of a pixel read the same inputs (one broadcast transaction), disjoint
-// 32-byte weight chunks from shared memory, and store 128 contiguous bytes per plane (round 1: one thread per pixel writing 512
-// scattered bytes in 16-byte pieces -- 5x off the kernel's HBM roofline, profiles/r02_launches_two_steps_32scenes.txt).
+// One thread per pixel computes the 64 output channels (input loads coalesced across the warp, weights broadcast from shared memory,
+// zero inputs skipped); the warp then transposes its 32 x 64 results through shared memory so that 8 lanes write the 128 contiguous
+// bytes of one pixel and plane (round 1 wrote 16-byte pieces at a 256-byte stride: 32 partial-sector transactions per store
+// instruction; an 8-lanes-per-pixel variant fixed the stores but multiplied the input loads by 8 and was 2.5x slower).
+static constexpr int CF_ROW = 68;                 // floats per staged pixel row (64 + 4: 16-byte aligned, conflict-free float4 columns)
+
 template <int COUT>
-__global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, int n, int cin, int h, int w,
+__global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict__ x, int n, int cin, int h, int w,
                                                          const float* __restrict__ wt,      // [9*cin][COUT]
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                                          __half* __restrict__ dst, int dst_ld, int dst_lo, int relu, int fmt) {
-    static_assert(COUT == 64, "8 lanes x 8 channels");
-    extern __shared__ float s_w[];                    // 9*cin*COUT weights, then scale, shift
+    static_assert(COUT == 64, "the staging tile is 64 channels wide");
+    extern __shared__ float s_w[];                    // 9*cin*COUT weights, scale, shift, then 4 warps x 32 x CF_ROW staging
     const int nw = 9 * cin * COUT;
     for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = wt[i];
     float* s_sc = s_w + nw; float* s_sh = s_sc + COUT;
     for (int i = threadIdx.x; i < COUT; i += blockDim.x) { s_sc[i] = scale[i]; s_sh[i] = shift[i]; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* tile = s_sh + COUT + warp * 32 * CF_ROW;
     __syncthreads();
     const size_t hw = (size_t)h * w;
     const size_t total = (size_t)n * hw;
-    const int c8 = threadIdx.x & 7;                   // this lane's channel octet
-    const size_t first = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3, stride = ((size_t)gridDim.x * blockDim.x) >> 3;
-    for (size_t pix = first; pix < total; pix += stride) {
-        const int img = (int)(pix / hw);
-        const int rem = (int)(pix - (size_t)img * hw);
-        const int y = rem / w, xx = rem - y * w;
-        float acc[8];
+    const size_t warp_stride = (size_t)gridDim.x * (blockDim.x >> 5) * 32;
+    for (size_t base = ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32; base < total; base += warp_stride) {
+        const size_t pix = base + lane;
+        if (pix < total) {
+            const int img = (int)(pix / hw);
+            const int rem = (int)(pix - (size_t)img * hw);
+            const int y = rem / w, xx = rem - y * w;
+            float acc[COUT];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = 0.0f;
-        const float* xin = x + (size_t)img * cin * hw;
-        for (int tap = 0; tap < 9; ++tap) {
-            const int yy = y + tap / 3 - 1, xc = xx + tap % 3 - 1;
-            if (yy < 0 || yy >= h || xc < 0 || xc >= w) continue;
-            for (int ci = 0; ci < cin; ++ci) {
-                const float v = __ldg(xin + (size_t)ci * hw + (size_t)yy * w + xc);
-                if (v == 0.0f) continue;                         // count images are sparse
-                const float4* wr = reinterpret_cast<const float4*>(s_w + (tap * cin + ci) * COUT + 8 * c8);
-                const float4 q0 = wr[0], q1 = wr[1];
-                acc[0] = fmaf(v, q0.x, acc[0]); acc[1] = fmaf(v, q0.y, acc[1]); acc[2] = fmaf(v, q0.z, acc[2]); acc[3] = fmaf(v, q0.w, acc[3]);
-                acc[4] = fmaf(v, q1.x, acc[4]); acc[5] = fmaf(v, q1.y, acc[5]); acc[6] = fmaf(v, q1.z, acc[6]); acc[7] = fmaf(v, q1.w, acc[7]);
+            for (int c = 0; c < COUT; ++c) acc[c] = 0.0f;
+            const float* xin = x + (size_t)img * cin * hw;
+            for (int tap = 0; tap < 9; ++tap) {
+                const int yy = y + tap / 3 - 1, xc = xx + tap % 3 - 1;
+                if (yy < 0 || yy >= h || xc < 0 || xc >= w) continue;
+                for (int ci = 0; ci < cin; ++ci) {
+                    const float v = __ldg(xin + (size_t)ci * hw + (size_t)yy * w + xc);
+                    if (v == 0.0f) continue;                         // count images are sparse
+                    const float4* wr = reinterpret_cast<const float4*>(s_w + (tap * cin + ci) * COUT);
+#pragma unroll
+                    for (int c4 = 0; c4 < COUT / 4; ++c4) {
+                        const float4 q = wr[c4];
+                        acc[4 * c4 + 0] = fmaf(v, q.x, acc[4 * c4 + 0]);
+                        acc[4 * c4 + 1] = fmaf(v, q.y, acc[4 * c4 + 1]);
+                        acc[4 * c4 + 2] = fmaf(v, q.z, acc[4 * c4 + 2]);
+                        acc[4 * c4 + 3] = fmaf(v, q.w, acc[4 * c4 + 3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c4 = 0; c4 < COUT / 4; ++c4) {
+                float4 o;
+                o.x = fmaf(acc[4 * c4 + 0], s_sc[4 * c4 + 0], s_sh[4 * c4 + 0]); o.y = fmaf(acc[4 * c4 + 1], s_sc[4 * c4 + 1], s_sh[4 * c4 + 1]);
+                o.z = fmaf(acc[4 * c4 + 2], s_sc[4 * c4 + 2], s_sh[4 * c4 + 2]); o.w = fmaf(acc[4 * c4 + 3], s_sc[4 * c4 + 3], s_sh[4 * c4 + 3]);
+                if (relu) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
+                *reinterpret_cast<float4*>(tile + lane * CF_ROW + 4 * c4) = o;
             }
         }
-        float f[8];
+        __syncwarp();
+        // 8 lanes per pixel, 4 pixels per pass: lane -> (pixel 4*it + lane/8, channel octet lane%8)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { f[j] = fmaf(acc[j], s_sc[8 * c8 + j], s_sh[8 * c8 + j]); if (relu) f[j] = fmaxf(f[j], 0.0f); }
-        if (dst_lo < 0) {                     // plain fp32 destination (train mode: the raw pre-BatchNorm tensor), row stride dst_ld floats
-            float4* of = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + pix * dst_ld + 8 * c8);
-            of[0] = make_float4(f[0], f[1], f[2], f[3]); of[1] = make_float4(f[4], f[5], f[6], f[7]);
-        } else {
-            store8(dst + pix * dst_ld, 8 * c8, dst_lo, fmt, f);
+        for (int it = 0; it < 8; ++it) {
+            const int pl = 4 * it + (lane >> 3), c8 = lane & 7;
+            const size_t pp = base + pl;
+            if (pp < total) {
+                const float4 a = *reinterpret_cast<const float4*>(tile + pl * CF_ROW + 8 * c8), b = *reinterpret_cast<const float4*>(tile + pl * CF_ROW + 8 * c8 + 4);
+                const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                if (dst_lo < 0) {                     // plain fp32 destination (train mode: the raw pre-BatchNorm tensor), row stride dst_ld floats
+                    float4* of = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + pp * dst_ld + 8 * c8);
+                    of[0] = a; of[1] = b;
+                } else {
+                    store8(dst + pp * dst_ld, 8 * c8, dst_lo, fmt, f);
+                }
+            }
         }
+        __syncwarp();
     }
 }
 
@@ -281,8 +310,9 @@ extern "C" int nbp_conv_first(const float* x, int n, int c_in, int h, int w, con
     if (rc) return rc;
     if ((uintptr_t)dst & 15) return invalid("nbp_conv_first: dst must be 16-byte aligned");
     if (dst_lo >= 0 && (rc = check_fmt("nbp_conv_first", fmt, fmt == 2 ? dst_lo : 64))) return rc;
-    const size_t smem = sizeof(float) * (size_t)(9 * c_in * 64 + 128);
-    conv_first_kernel<64><<<grid_for((size_t)n * h * w * 8, 256), 256, smem, (cudaStream_t)stream>>>(x, n, c_in, h, w, weight, scale, shift,
+    const size_t smem = sizeof(float) * (size_t)(9 * c_in * 64 + 128 + 4 * 32 * CF_ROW);
+    if (smem > 48 * 1024) return invalid("nbp_conv_first: c_in=%d needs more than 48 KB of shared memory", c_in);
+    conv_first_kernel<64><<<grid_for((size_t)n * h * w, 128), 128, smem, (cudaStream_t)stream>>>(x, n, c_in, h, w, weight, scale, shift,
                                                                                                   (__half*)dst, dst_ld, dst_lo, relu, fmt);
     count_launch();
     return check_cuda(cudaGetLastError(), "nbp_conv_first launch");
