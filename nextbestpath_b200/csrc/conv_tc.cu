@@ -74,6 +74,7 @@ struct ConvKParams {
     int dst_fmt, pool_fmt;              // second-plane format written by the epilogue: 1 = fp16 lo*2048, 2 = e4m3 pair (MODE 2 consumers)
     int cluster;                        // 1, or 2: CTA pairs (thread-block cluster) work on two m-tiles of the SAME n-tile in lock step and each
                                         // loads half of every weight tile, multicast into both CTAs' shared memory (half the L2->SM weight bytes)
+    int dbg_skip_epilogue;
     int interleave;                     // MODE 2: 1 (default) = alternate the fp16 and e4m3 UMMAs per 16-element K step, 0 = two runs per stage
     unsigned long long* sat_count;      // optional: += number of (pixel, 32-channel group) stores in which an e4m3 value saturated
     int out_f32;                        // 1: the destination is plain fp32 NHWC (gradients), no fp16 planes
@@ -120,17 +121,11 @@ struct ConvCfg {
     // alignment of the dynamic shared-memory window (checked at run time) instead of reserving an alignment slack: 3 KB + 7 x 32 KB is
     // exactly the 227 KB limit for 128-column tiles
     static constexpr int AUX_FRONT = 3072;
-    // epilogue staging: every epilogue warp transposes its 32 pixels x 32 channels (64 B per plane) through shared memory so that four
-    // lanes write the 64 contiguous bytes of one pixel and plane (full sectors); row pitch 80 B keeps the 16-byte accesses conflict-free
-    static constexpr int EPI_ROW = 80;
-    static constexpr int EPI_WARP = 2 * 32 * EPI_ROW;                     // two planes
-    static constexpr int EPI_BYTES = 4 * EPI_WARP;                        // 20 KB
-    static constexpr int STAGES_RAW = SPLIT ? (SMEM_LIMIT - AUX_FRONT - EPI_BYTES) / STAGE_BYTES
-                                            : (SMEM_LIMIT - SMEM_AUX - 1024 - EPI_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES_RAW = SPLIT ? (SMEM_LIMIT - AUX_FRONT) / STAGE_BYTES : (SMEM_LIMIT - SMEM_AUX - 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > (PAIR ? 9 : 8) ? (PAIR ? 9 : 8) : STAGES_RAW;
     static constexpr int ACC_COLS = PLANES * BLOCK_N;                     // acc_hi [, acc_lo] columns per buffer
     static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = EPI_BYTES + (SPLIT ? AUX_FRONT + STAGES * STAGE_BYTES : STAGES * STAGE_BYTES + SMEM_AUX + 1024);   // +1024: manual 1024-B alignment
+    static constexpr int SMEM_BYTES = SPLIT ? AUX_FRONT + STAGES * STAGE_BYTES : STAGES * STAGE_BYTES + SMEM_AUX + 1024;   // +1024: manual 1024-B alignment
     static_assert(!SPLIT || (2 * STAGES + 4) * 8 + 8 <= 512, "barriers overflow their slot");
     static_assert(!SPLIT || 512 + 2 * 2 * BLOCK_N * 4 <= AUX_FRONT, "affine staging overflows the front block");
     static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
@@ -160,7 +155,6 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     uint64_t* tempty_bar = tfull_bar + 2;                               // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     float* s_affine = reinterpret_cast<float*>(aux + 512);              // [2 acc][2][BLOCK_N]
-    uint8_t* s_epi = SPLIT ? smem + STAGES * Cfg::STAGE_BYTES : aux + SMEM_AUX;   // [4 epilogue warps][2 planes][32 pixels][EPI_ROW]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -457,21 +451,9 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             const size_t opix = (size_t)((size_t)nn * oh + oy) * ow + ox;
             float* orow_f = reinterpret_cast<float*>(p.dst) + opix * p.dst_ld + p.dst_c_off + n_tile * BLOCK_N;
 
-            // coalesced stores: in pass t (0..3) this lane writes the 16-byte chunk (lane & 3) of tile pixel q*32 + 8t + (lane >> 2)
-            size_t st_pix[4]; bool st_ok[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int m2 = q * 32 + 8 * t + (lane >> 2);
-                const int wi2 = m2 % p.tw, hi2 = (m2 / p.tw) % p.th, ni2 = m2 / (p.tw * p.th);
-                const int x2 = tx * p.tw + wi2, y2 = ty * p.th + hi2, n2 = tb * p.tn + ni2;
-                st_ok[t] = x2 < p.w && y2 < p.h && n2 < p.n && !ghost;
-                const int oy2 = p.up2x ? 2 * y2 + (parity >> 1) : y2, ox2 = p.up2x ? 2 * x2 + (parity & 1) : x2;
-                st_pix[t] = ((size_t)n2 * oh + oy2) * ow + ox2;
-            }
-            uint8_t* epi = s_epi + q * Cfg::EPI_WARP;
-
             // affine + activation + store of 32 consecutive output channels held as fp32 in v[]
             auto finish = [&](int c, const float* v) {
+                if (p.dbg_skip_epilogue) return;         // timing experiment only (NBP_CONV_EPI_SKIP=1): how much of a launch is epilogue-bound
                 if (p.out_f32) {                     // dgrad: fp32 NHWC destination
                     if (valid) {
 #pragma unroll
@@ -543,58 +525,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                         for (int j = 0; j < 4; ++j) ol[j] = make_uint4(packed_lo[4 * j], packed_lo[4 * j + 1], packed_lo[4 * j + 2], packed_lo[4 * j + 3]);
                     }
                 };
-                {
-                    // hi plane and second plane of this lane's pixel -> its staging rows; then 4 passes of 8 pixels x 4 chunks
-                    const int ch = p.dst_c_off + n_tile * BLOCK_N + c * 32;
-                    uint32_t w0[16], w1[16];
-                    bool sat = false;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const __half2 h = __floats2half2_rn(a[2 * j], a[2 * j + 1]);
-                        w0[j] = *reinterpret_cast<const uint32_t*>(&h);
-                        if (PRECISE) {
-                            const float2 hf = __half22float2(h);
-                            if (p.dst_fmt == 2) {
-                                const uint32_t qh = e4m3x2(a[2 * j] * NBP_E4M3_ACT_SCALE, a[2 * j + 1] * NBP_E4M3_ACT_SCALE);
-                                const uint32_t ql = e4m3x2((a[2 * j] - hf.x) * (2048.0f * NBP_E4M3_ACT_SCALE), (a[2 * j + 1] - hf.y) * (2048.0f * NBP_E4M3_ACT_SCALE));
-                                sat |= fmaxf(fabsf(a[2 * j]), fabsf(a[2 * j + 1])) > NBP_E4M3_MAX / NBP_E4M3_ACT_SCALE;
-                                // staging row of the second plane: bytes [0,32) e4m3(x/8) of the 32 channels, [32,64) e4m3 of the residuals
-                                if (j & 1) { w1[j >> 1] |= qh << 16; w1[8 + (j >> 1)] |= ql << 16; } else { w1[j >> 1] = qh; w1[8 + (j >> 1)] = ql; }
-                            } else {
-                                const __half2 l = __floats2half2_rn((a[2 * j] - hf.x) * 2048.0f, (a[2 * j + 1] - hf.y) * 2048.0f);
-                                w1[j] = *reinterpret_cast<const uint32_t*>(&l);
-                            }
-                        }
-                    }
-                    if (sat && valid && p.sat_count) atomicAdd(p.sat_count, 1ull);        // rare by construction: out-of-range inputs only
-                    uint4* r0 = reinterpret_cast<uint4*>(epi + lane * Cfg::EPI_ROW);
-                    uint4* r1 = reinterpret_cast<uint4*>(epi + 32 * Cfg::EPI_ROW + lane * Cfg::EPI_ROW);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        r0[j] = make_uint4(w0[4 * j], w0[4 * j + 1], w0[4 * j + 2], w0[4 * j + 3]);
-                        if (PRECISE) r1[j] = make_uint4(w1[4 * j], w1[4 * j + 1], w1[4 * j + 2], w1[4 * j + 3]);
-                    }
-                    __syncwarp();
-                    const int cc = lane & 3;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const int pl = 8 * t + (lane >> 2);
-                        if (st_ok[t] && p.dbg_skip_epilogue != 2) {
-                            __half* pix = p.dst + st_pix[t] * p.dst_ld;
-                            *reinterpret_cast<uint4*>(pix + ch + 8 * cc) = *reinterpret_cast<const uint4*>(epi + pl * Cfg::EPI_ROW + 16 * cc);
-                            if (PRECISE) {
-                                const uint4 sv = *reinterpret_cast<const uint4*>(epi + 32 * Cfg::EPI_ROW + pl * Cfg::EPI_ROW + 16 * cc);
-                                if (p.dst_fmt == 2) {
-                                    uint8_t* g = reinterpret_cast<uint8_t*>(pix + p.dst_lo_off) + (ch >> 6) * 128 + (ch & 63);
-                                    *reinterpret_cast<uint4*>(g + (cc < 2 ? 16 * cc : 64 + 16 * (cc - 2))) = sv;
-                                } else {
-                                    *reinterpret_cast<uint4*>(pix + ch + p.dst_lo_off + 8 * cc) = sv;
-                                }
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
+                if (valid) split_store(p.dst + opix * p.dst_ld, p.dst_c_off + n_tile * BLOCK_N + c * 32, p.dst_lo_off, p.dst_fmt, a);
                 if (p.pool) {
                     // fused nn.MaxPool2d(2,2): the 2x2 window of a pixel lives in lanes {l, l^1, l^tw, l^(tw+1)} of this warp (tile rows
                     // are tw <= 16 pixels wide and a warp holds 32 consecutive tile pixels); max commutes with the monotonic hi/lo split
@@ -840,6 +771,7 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     if (inter_env < 0) { const char* e = getenv("NBP_CONV_INTERLEAVE"); inter_env = e ? atoi(e) : 1; }
     if (k8_env < 0) { const char* e = getenv("NBP_CONV_KCHUNK_E4M3"); k8_env = e ? atoi(e) : 0; }
     kp.interleave = inter_env;
+    { static int sk = -1; if (sk < 0) { const char* e = getenv("NBP_CONV_EPI_SKIP"); sk = e ? atoi(e) : 0; } kp.dbg_skip_epilogue = sk; }
     if (halo_env < 0) { const char* e = getenv("NBP_CONV_HALO"); halo_env = e ? atoi(e) : 1; }
     if (kchunk_env < 0) { const char* e = getenv("NBP_CONV_KCHUNK"); kchunk_env = e ? atoi(e) : 8; }
     // K slices (64 elements each) per in-TMEM accumulation chain; 0 = unbounded.  The fp16+e4m3 mode keeps whole reductions in TMEM by
