@@ -74,7 +74,6 @@ struct ConvKParams {
     int dst_fmt, pool_fmt;              // second-plane format written by the epilogue: 1 = fp16 lo*2048, 2 = e4m3 pair (MODE 2 consumers)
     int cluster;                        // 1, or 2: CTA pairs (thread-block cluster) work on two m-tiles of the SAME n-tile in lock step and each
                                         // loads half of every weight tile, multicast into both CTAs' shared memory (half the L2->SM weight bytes)
-    int dbg_skip_epilogue;
     int interleave;                     // MODE 2: 1 (default) = alternate the fp16 and e4m3 UMMAs per 16-element K step, 0 = two runs per stage
     unsigned long long* sat_count;      // optional: += number of (pixel, 32-channel group) stores in which an e4m3 value saturated
     int out_f32;                        // 1: the destination is plain fp32 NHWC (gradients), no fp16 planes
@@ -453,7 +452,6 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 
             // affine + activation + store of 32 consecutive output channels held as fp32 in v[]
             auto finish = [&](int c, const float* v) {
-                if (p.dbg_skip_epilogue) return;         // timing experiment only (NBP_CONV_EPI_SKIP=1): how much of a launch is epilogue-bound
                 if (p.out_f32) {                     // dgrad: fp32 NHWC destination
                     if (valid) {
 #pragma unroll
@@ -771,7 +769,6 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     if (inter_env < 0) { const char* e = getenv("NBP_CONV_INTERLEAVE"); inter_env = e ? atoi(e) : 1; }
     if (k8_env < 0) { const char* e = getenv("NBP_CONV_KCHUNK_E4M3"); k8_env = e ? atoi(e) : 0; }
     kp.interleave = inter_env;
-    { static int sk = -1; if (sk < 0) { const char* e = getenv("NBP_CONV_EPI_SKIP"); sk = e ? atoi(e) : 0; } kp.dbg_skip_epilogue = sk; }
     if (halo_env < 0) { const char* e = getenv("NBP_CONV_HALO"); halo_env = e ? atoi(e) : 1; }
     if (kchunk_env < 0) { const char* e = getenv("NBP_CONV_KCHUNK"); kchunk_env = e ? atoi(e) : 8; }
     // K slices (64 elements each) per in-TMEM accumulation chain; 0 = unbounded.  The fp16+e4m3 mode keeps whole reductions in TMEM by
