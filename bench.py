@@ -24,6 +24,7 @@ cpu_baseline: the oracle (CPU restatement of the reference path; the reference's
 extra blocks (reported baselines / secondary configs, each outside the two timed regions above):
   latency_b1     : NBP.forward at batch 1 (BASELINE configs[0]: the reference calls the net with one scene), 128^2 and 256^2
   cudnn_baseline : the same network under torch + cuDNN on this GPU (fp32 with TF32 off, and TF32 on), "the kernel to beat"
+  configs3_reduced: BASELINE configs[3] shape (AiMDoom-insane-shaped meshes, 512x512 grid) at 8 rollouts per GPU
   train          : BASELINE configs[2] shape -- NBP fwd + loss + bwd + AdamW on 256^2 tiles, 64 tiles per GPU per optimizer
                    step, NCCL all-reduce of the flat gradient across the N ranks
 """
@@ -379,6 +380,7 @@ def run_ours(args):
     del eng, moves
     torch.cuda.empty_cache()
     latency = None if args.no_extras else latency_b1(net, dev)
+    cfg3 = None if args.no_extras else cfg3_block(args, dev, world, rank, net, max_over_ranks, barrier)
     train = None if args.no_extras else train_block(args, dev, world, rank, max_over_ranks, barrier)
     cudnn = None
     if rank == 0 and world == 1 and not args.no_extras:
@@ -425,7 +427,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "stage_ms": stage_ms,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "latency_b1": latency, "cudnn_baseline": cudnn, "train": train}
+            "latency_b1": latency, "cudnn_baseline": cudnn, "train": train, "configs3_reduced": cfg3}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -511,6 +513,40 @@ def cudnn_baseline(net, dev, B_total, S, chunk, our_value):
     res["note"] = (f"eval forward of {chunk} scenes at {S}x{S}, torch {torch.__version__} / cuDNN {torch.backends.cudnn.version()}, "
                    "cudnn.benchmark on, same weights and input; the parity bar (1e-3) is met by ours and by cuDNN fp32 only")
     return res
+
+
+def cfg3_block(args, dev, world, rank, net, max_over_ranks, barrier):
+    """BASELINE configs[3] shape at reduced scene count: AiMDoom-insane-shaped meshes (~50 k triangles), 512x512 grid, 8 rollouts per
+    GPU (the full configuration is 128 rollouts across 4 GPUs = 32 per GPU; 8 scenes at 512^2 are one network chunk, the same tensor
+    sizes as 32 scenes at 256^2).  Same engine, same network module (its graph for the new shape is captured in the warm-up)."""
+    from nextbestpath_b200.rollout import RolloutEngine
+    n_sc, prefill, warm, steps, S = 8, 20, 2, 3, 512
+    scenes, poses, az = make_workload(n_sc, "insane", prefill + warm + steps + 4, rank0_scene_index=rank * n_sc, seed0=5000)
+    eng = RolloutEngine(scenes, net, dev, S=S, max_steps=prefill + warm + steps + 3, seed=9)
+    eng.reset(poses[:, 0])
+    t = 0
+    for _ in range(prefill):
+        eng.step(eng.upload_move(poses[:, t], poses[:, t + 1], az[:, t], az[:, t + 1]), run_network=False)
+        t += 1
+    moves = [eng.upload_move(poses[:, t + i], poses[:, t + i + 1], az[:, t + i], az[:, t + i + 1]) for i in range(warm + steps)]
+    for i in range(warm):
+        eng.step(moves[i])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(warm, warm + steps):
+        eng.step(moves[i])
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    out = {"metric": METRIC, "value": world * n_sc * steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "ms_per_step": ms / steps,
+           "scenes_per_gpu": n_sc, "grid": f"{S}x{S}", "mesh_level": "insane", "mean_faces_per_scene": float(np.mean([s.n_faces for s in scenes])),
+           "prefill_pose": prefill, "mean_cloud_points_per_scene": float(eng.cloud_len.float().mean().item()), "steps": steps,
+           "algorithmic_tflops_network": world * n_sc * steps * FLOP_PER_SCENE_STEP[S] / (ms * 1e-3) / 1e12,
+           "workload": f"BASELINE configs[3] shape, reduced to {world * n_sc} rollouts on {world} GPU (full: 128 rollouts across 4 GPUs)"}
+    del eng, moves
+    torch.cuda.empty_cache()
+    return out
 
 
 def train_block(args, dev, world, rank, max_over_ranks, barrier):
