@@ -83,6 +83,9 @@ CASES = [
     (1, 16, 48, 64, 0, 256, 9),        # non-square, two N tiles
     (5, 4, 4, 192, 0, 64, 9),          # tiny image: 8 images per tile, 3 K-chunks per tap
     (1, 64, 64, 64, 0, 64, 9),         # more tiles than one wave of K stages
+    (3, 8, 16, 128, 0, 128, 9),        # 3 m-tiles: the CTA pair of the last one runs a ghost tile (128-column pair kernel)
+    (3, 8, 16, 64, 0, 64, 9),          # same for the 64-channel halo pair kernel
+    (7, 16, 16, 64, 64, 128, 1),       # 14 m-tiles over 7 pairs, 1x1 over two sources
 ]
 
 
@@ -318,7 +321,8 @@ def _from_act_fmt2(t, c):
 
 @pytest.mark.parametrize("n,h,w,c0,c1,cout,taps,up", [(2, 16, 16, 64, 0, 64, 9, 0), (1, 32, 32, 128, 0, 128, 9, 0), (3, 8, 8, 64, 0, 128, 9, 0),
                                                        (2, 16, 16, 128, 128, 64, 1, 0), (1, 32, 32, 64, 64, 32, 1, 0), (1, 16, 48, 128, 0, 256, 9, 0),
-                                                       (5, 4, 4, 192, 0, 64, 9, 0), (2, 16, 16, 128, 0, 64, 4, 1), (1, 8, 8, 256, 0, 128, 4, 1)])
+                                                       (5, 4, 4, 192, 0, 64, 9, 0), (2, 16, 16, 128, 0, 64, 4, 1), (1, 8, 8, 256, 0, 128, 4, 1),
+                                                       (3, 8, 16, 128, 0, 128, 9, 0), (3, 8, 16, 64, 0, 64, 9, 0), (3, 8, 16, 64, 0, 64, 4, 1)])
 def test_conv_fwd_e4m3_correction_mode(n, h, w, c0, c1, cout, taps, up):
     """nbp_conv_desc mode 2: hi product on the fp16 pipe, both correction products as one e4m3 reduction.  Checked against the same
     arithmetic evaluated in float64 from the quantised operands (exact up to the tensor core's accumulation), for plain, concat,
