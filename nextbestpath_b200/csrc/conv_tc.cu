@@ -666,8 +666,11 @@ static int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
 template <int BLOCK_N, int MODE, int HALO = 0, bool PAIR = false>
 static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvKParams& kp, int sms, cudaStream_t st) {
     using Cfg = ConvCfg<BLOCK_N, MODE, HALO, PAIR>;
-    static bool attr_set = false;
-    static int max_clusters2 = 0;          // co-resident 2-CTA clusters of this instantiation (0 = not queried yet)
+    static bool attr_set_d[NBP_MAX_DEVICES] = {};
+    static int max_clusters2_d[NBP_MAX_DEVICES] = {};   // co-resident 2-CTA clusters of this instantiation (0 = not queried yet)
+    const int dslot = device_slot();
+    bool& attr_set = attr_set_d[dslot];
+    int& max_clusters2 = max_clusters2_d[dslot];
     auto kern = conv_gemm_f16<BLOCK_N, MODE, HALO, PAIR>;
     if (!attr_set) {
         int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES),
@@ -830,7 +833,8 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     rc = make_weight_map(&b, d->weight, d->taps * (d->c0 + d->c1), (d->up2x ? 4 : 1) * planes * d->c_out, pair ? block_n / 2 : (split ? 1 : planes) * block_n / kp.cluster);
     if (rc) return rc;
 
-    static int sms = 0;
+    static int sms_d[NBP_MAX_DEVICES] = {};
+    int& sms = sms_d[device_slot()];
     if (!sms) {
         int dev = 0;
         rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");

@@ -13,6 +13,15 @@ int check_cuda(cudaError_t e, const char* what);      // 0 or positive CUDA erro
 int invalid(const char* fmt, ...);                    // always returns NBP_ERR_INVALID
 void count_launch(uint64_t n = 1);                    // nbp_launch_count accounting
 
+// One-time per-DEVICE state (function attributes, SM counts): a process may drive several GPUs, and cudaFuncSetAttribute /
+// occupancy results belong to the device that was current when they were made.
+static constexpr int NBP_MAX_DEVICES = 64;
+inline int device_slot() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d >= 0 && d < NBP_MAX_DEVICES) ? d : 0;
+}
+
 // Pinned fp32 arithmetic: one IEEE rounding per operation, never contracted into FMA, so that
 // results are bit-identical to the strict-fp32 CPU oracle (oracle/raster_oracle.c, oracle/oracle.py).
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }

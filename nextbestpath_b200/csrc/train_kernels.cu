@@ -752,7 +752,8 @@ extern "C" int nbp_bn_bwd_split(const float* dy, int ld_dy, const void* z, int l
     if (rc) return rc;
     if (amax) { rc = check_cuda(cudaMemsetAsync(amax, 0, sizeof(float), ST), "memset"); if (rc) return rc; }
     const size_t smem = sizeof(float) * ((size_t)(256 / (C / 8)) * 2 * C + 4 * (size_t)C);
-    static bool attr = false;
+    static bool attr_d[NBP_MAX_DEVICES] = {};
+    bool& attr = attr_d[device_slot()];
     if (!attr) {
         cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         cudaFuncSetAttribute(bn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 2048 * 4);
@@ -855,7 +856,8 @@ extern "C" int nbp_stem_wgrad(const float* x, int n, int c_in, int h, int w, con
     const size_t nacc = (size_t)9 * c_in * 64;
     int rc = check_cuda(cudaMemsetAsync(workspace, 0, sizeof(double) * nacc, ST), "memset");
     if (rc) return rc;
-    static bool attr = false;
+    static bool attr_d[NBP_MAX_DEVICES] = {};
+    bool& attr = attr_d[device_slot()];
     if (!attr) { cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 16 * 64 * 4); attr = true; }
     stem_wgrad_kernel<<<148 * 2, 256, sizeof(float) * nacc, ST>>>(x, n, c_in, h, w, dz, workspace);
     d2f_kernel<<<tk_grid(nacc, 256), 256, 0, ST>>>(workspace, dweight, nacc, 1.0f, 1);

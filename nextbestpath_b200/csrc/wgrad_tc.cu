@@ -227,7 +227,8 @@ static int make_nhwc_map(CUtensorMap* m, const void* ptr, int span, int ld, int 
 template <int BLOCK_N>
 static int launch_wgrad(const CUtensorMap& r, const CUtensorMap& c, const WgradParams& p, int sms, cudaStream_t st) {
     using Cfg = WgCfg<BLOCK_N>;
-    static bool attr = false;
+    static bool attr_d[NBP_MAX_DEVICES] = {};
+    bool& attr = attr_d[device_slot()];
     if (!attr) {
         int rc = check_cuda(cudaFuncSetAttribute(wgrad_gemm_f16x2<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES), "cudaFuncSetAttribute(wgrad)");
         if (rc) return rc;
@@ -277,7 +278,8 @@ extern "C" int nbp_conv_wgrad(const void* dz, int c_out, int ld_dz, int lo_dz, c
     if (x_rows) { p.stride_m = 1; p.stride_n = ktc; } else { p.stride_m = ktc; p.stride_n = 1; }
     p.stride_tap = c_in;
     p.inv_scale = inv_scale; p.out = dweight;
-    static int sms = 0;
+    static int sms_d[NBP_MAX_DEVICES] = {};
+    int& sms = sms_d[device_slot()];
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     const int out_tiles = p.m_tiles * p.n_tiles * taps;
     int splits = (2 * sms + out_tiles - 1) / out_tiles;
