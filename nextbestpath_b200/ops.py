@@ -53,6 +53,7 @@ class _Workspace:
 
 
 _ws = _Workspace()
+RASTER_MAX_VIEW_FACES = 6_000_000      # (view, face) pairs per rasteriser call: bounds its scratch at 4.3 GB
 
 
 def raster_depth(verts, faces, vert_offsets, face_offsets, view_scene, R, T, H, W, face_counts_host,
@@ -73,13 +74,22 @@ def raster_depth(verts, faces, vert_offsets, face_offsets, view_scene, R, T, H, 
     if want_faces and pix_to_face is None:
         pix_to_face = torch.empty((n_views, H, W), dtype=torch.int32, device=dev)
     L = _lib.lib()
-    need = L.nbp_raster_workspace_bytes(n_views, total)
-    ws = _ws.get("raster", need, dev)
-    rc = L.nbp_raster_depth_batched(_ptr(verts), _ptr(faces), _ptr(vert_offsets), _ptr(face_offsets), n_scenes,
-                                    _ptr(view_scene), _ptr(R), _ptr(T), n_views, total, max_f, H, W,
-                                    tan_half_fov(fov_deg), z_clip, _ptr(zbuf), _ptr(pix_to_face),
-                                    _ptr(ws), ws.numel(), _stream())
-    _lib.check(rc, "nbp_raster_depth_batched")
+    # the rasteriser's scratch is 720 bytes per (view, face) pair: views are independent, so large batches go through in groups that
+    # keep it under RASTER_MAX_VIEW_FACES pairs (4.3 GB) instead of reserving e.g. 18 GB for 512 views of 50 k-triangle meshes
+    v0 = 0
+    while v0 < n_views:
+        v1, pairs = v0, 0
+        while v1 < n_views and (v1 == v0 or pairs + face_counts_host[view_scene_host[v1]] <= RASTER_MAX_VIEW_FACES):
+            pairs += face_counts_host[view_scene_host[v1]]
+            v1 += 1
+        ws = _ws.get("raster", L.nbp_raster_workspace_bytes(v1 - v0, pairs), dev)
+        rc = L.nbp_raster_depth_batched(_ptr(verts), _ptr(faces), _ptr(vert_offsets), _ptr(face_offsets), n_scenes,
+                                        _ptr(view_scene[v0:v1]), _ptr(R[v0:v1]), _ptr(T[v0:v1]), v1 - v0, pairs, max_f, H, W,
+                                        tan_half_fov(fov_deg), z_clip, _ptr(zbuf[v0:v1]),
+                                        _ptr(pix_to_face[v0:v1]) if pix_to_face is not None else None,
+                                        _ptr(ws), ws.numel(), _stream())
+        _lib.check(rc, "nbp_raster_depth_batched")
+        v0 = v1
     return (zbuf, pix_to_face) if want_faces else zbuf
 
 

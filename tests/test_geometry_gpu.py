@@ -64,6 +64,23 @@ def test_raster_bit_exact_vs_oracle(H, W):
     assert hit > 0.5 * len(view_scene) * H * W          # the views actually see geometry
 
 
+def test_raster_view_groups_bound_the_workspace(monkeypatch):
+    """ops.raster_depth sends large batches through in groups of views (RASTER_MAX_VIEW_FACES): same frames, bounded scratch."""
+    scenes = [syn.make_scene(4, tri_budget=900), syn.make_scene(5, tri_budget=2500)]
+    view_scene, poses = [], []
+    for si, sc in enumerate(scenes):
+        p, _ = syn.random_walk(sc, 4, seed=20 + si)
+        for q in p:
+            view_scene.append(si); poses.append(q)
+    R, T = _cams(np.stack(poses))
+    z0, f0 = _render_gpu(scenes, view_scene, R, T, 64, 114)
+    monkeypatch.setattr(ops, "RASTER_MAX_VIEW_FACES", 3000)            # 1-3 views per call
+    ops._ws.bufs.pop(("raster", z0.device), None)
+    z1, f1 = _render_gpu(scenes, view_scene, R, T, 64, 114)
+    assert torch.equal(z0, z1) and torch.equal(f0, f1)
+    assert ops._ws.bufs[("raster", z0.device)].numel() <= ops._lib.lib().nbp_raster_workspace_bytes(3, 3000 + 2600)
+
+
 def test_raster_edge_cases():
     R, T = torch.eye(3)[None], torch.zeros(1, 3)
     # empty mesh: every pixel is a miss
