@@ -455,13 +455,12 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                 if (p.out_f32) {                     // dgrad: fp32 NHWC destination
                     if (valid) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 o4;
-                            o4.x = fmaf(v[4 * j + 0], sa[c * 32 + 4 * j + 0], sa[BLOCK_N + c * 32 + 4 * j + 0]);
-                            o4.y = fmaf(v[4 * j + 1], sa[c * 32 + 4 * j + 1], sa[BLOCK_N + c * 32 + 4 * j + 1]);
-                            o4.z = fmaf(v[4 * j + 2], sa[c * 32 + 4 * j + 2], sa[BLOCK_N + c * 32 + 4 * j + 2]);
-                            o4.w = fmaf(v[4 * j + 3], sa[c * 32 + 4 * j + 3], sa[BLOCK_N + c * 32 + 4 * j + 3]);
-                            reinterpret_cast<float4*>(orow_f + c * 32)[j] = o4;
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t o8[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                o8[e] = __float_as_uint(fmaf(v[8 * j + e], sa[c * 32 + 8 * j + e], sa[BLOCK_N + c * 32 + 8 * j + e]));
+                            st_global_32B(orow_f + c * 32 + 8 * j, o8);
                         }
                     }
                     return;
@@ -493,13 +492,9 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                             sat |= fmaxf(fabsf(x[2 * j]), fabsf(x[2 * j + 1])) > NBP_E4M3_MAX / NBP_E4M3_ACT_SCALE;
                             if (j & 1) { p8h[j >> 1] |= qh << 16; p8l[j >> 1] |= ql << 16; } else { p8h[j >> 1] = qh; p8l[j >> 1] = ql; }
                         }
-                        uint4* o = reinterpret_cast<uint4*>(pix + ch);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) o[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                        st_global_32B(pix + ch, packed); st_global_32B(pix + ch + 16, packed + 8);
                         uint8_t* g = reinterpret_cast<uint8_t*>(pix + lo_off) + (ch >> 6) * 128 + (ch & 63);
-                        uint4* oh = reinterpret_cast<uint4*>(g); uint4* ol = reinterpret_cast<uint4*>(g + 64);
-                        oh[0] = make_uint4(p8h[0], p8h[1], p8h[2], p8h[3]); oh[1] = make_uint4(p8h[4], p8h[5], p8h[6], p8h[7]);
-                        ol[0] = make_uint4(p8l[0], p8l[1], p8l[2], p8l[3]); ol[1] = make_uint4(p8l[4], p8l[5], p8l[6], p8l[7]);
+                        st_global_32B(g, p8h); st_global_32B(g + 64, p8l);
                         if (sat && p.sat_count) atomicAdd(p.sat_count, 1ull);          // rare by construction: out-of-range inputs only
                         return;
                     }
@@ -514,14 +509,8 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                             packed_lo[j] = *reinterpret_cast<const uint32_t*>(&l);
                         }
                     }
-                    uint4* o = reinterpret_cast<uint4*>(pix + ch);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) o[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                    if (PRECISE) {
-                        uint4* ol = reinterpret_cast<uint4*>(pix + ch + lo_off);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) ol[j] = make_uint4(packed_lo[4 * j], packed_lo[4 * j + 1], packed_lo[4 * j + 2], packed_lo[4 * j + 3]);
-                    }
+                    st_global_32B(pix + ch, packed); st_global_32B(pix + ch + 16, packed + 8);
+                    if (PRECISE) { st_global_32B(pix + ch + lo_off, packed_lo); st_global_32B(pix + ch + lo_off + 16, packed_lo + 8); }
                 };
                 if (valid) split_store(p.dst + opix * p.dst_ld, p.dst_c_off + n_tile * BLOCK_N + c * 32, p.dst_lo_off, p.dst_fmt, a);
                 if (p.pool) {
