@@ -60,7 +60,16 @@ static constexpr int BLOCK_K = 64;                         // fp16 elements = on
 static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;     // one plane of a plain 128-pixel A block
 static constexpr int HALO_ROWS = 160;                          // (th + 2) * tw pixels of a halo block (tw = 16, th = 8)
 static constexpr int A_HALO_BYTES = HALO_ROWS * BLOCK_K * 2;   // one plane of a halo A block
-static constexpr int CONV_THREADS = 256;
+#ifndef NBP_EPI_WARPS
+#define NBP_EPI_WARPS 8
+#endif
+// warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = epilogue.  An epilogue warp may only read the TMEM lane quarter (warp & 3), so
+// warps 2,3,4,5 cover the 128 accumulator rows once; with 8 warps two warps share each quarter (and each scheduler) and take alternate
+// 32-column groups -- one warp per scheduler cannot hide the latencies of the epilogue (TMEM loads, shuffles, stores that wait for the LSU)
+static constexpr int EPI_WARPS = NBP_EPI_WARPS;
+static constexpr int EPI_SPLIT = EPI_WARPS / 4;                 // warps sharing one lane quarter
+static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "4 or 8 epilogue warps");
+static constexpr int CONV_THREADS = 64 + 32 * EPI_WARPS;
 static constexpr int SMEM_LIMIT = 232448;                  // 227 KB opt-in maximum per CTA
 static constexpr int SMEM_AUX = 4096;                      // barriers + tmem ptr + scale/shift staging
 
@@ -168,7 +177,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         // a slot is free again when the MMAs of EVERY CTA of the cluster have read it (peers multicast weight tiles into it)
         // PAIR: the even CTA's full barrier collects one arrival per CTA (+ both CTAs' bytes), its MMAs release the slot in both CTAs
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], PAIR ? 2u : 1u); mbar_init(&empty_bar[s], PAIR ? 1u : (uint32_t)CL); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], PAIR ? 8 : 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], (PAIR ? 2 : 1) * EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 2) { if (PAIR) tmem_alloc_pair(tmem_ptr, Cfg::TMEM_COLS); else tmem_alloc(tmem_ptr, Cfg::TMEM_COLS); }
@@ -412,11 +421,14 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
               }
             }
         }
-    } else if (warp >= 4) {
-        // ================================================================= epilogue (4 warps = 128 TMEM lanes)
+    } else if (warp >= 2) {
+        // ================================================================= epilogue (128 TMEM lanes x EPI_SPLIT column-group sets)
         const int q = warp & 3;                                 // TMEM lane quarter this warp may access
+        const int cg0 = (warp - 2) >> 2;                        // first 32-column group of this warp (then every EPI_SPLIT-th)
         const int m = q * 32 + lane;                            // accumulator row = pixel of the tile
-        const int et = threadIdx.x - 128;                       // 0..127
+        const int et = threadIdx.x - 64;                        // 0 .. 32 * EPI_WARPS - 1
+        const uint32_t s_affine_addr = smem_u32(s_affine);
+        int staged_n_tile = -1;
         int acc = 0; uint32_t acc_phase = 0;
         int tsel = 0;
         const int n_chunks = (num_k + p.kchunk - 1) / p.kchunk;
@@ -437,29 +449,37 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             const int oh = p.up2x ? 2 * p.h : p.h, ow = p.up2x ? 2 * p.w : p.w;
             const int oy = p.up2x ? 2 * y + (parity >> 1) : y, ox = p.up2x ? 2 * x + (parity & 1) : x;
 
-            // stage this tile's affine into smem (two buffers alternate per tile: the previous user of a buffer finished
-            // two tiles ago, and the named barrier below orders the writes before the reads)
-            float* sa = s_affine + tsel * 2 * BLOCK_N;
-            tsel ^= 1;
-            for (int i = et; i < BLOCK_N; i += 128) {
-                sa[i] = p.scale[n_tile * BLOCK_N + i];
-                sa[BLOCK_N + i] = p.shift[n_tile * BLOCK_N + i];
+            // stage the n-tile's affine into smem when it changes (two buffers alternate per change: every warp that still reads the
+            // buffer being rewritten has yet to pass the previous change's barrier, which the writer is already behind)
+            if (n_tile != staged_n_tile) {
+                staged_n_tile = n_tile;
+                tsel ^= 1;
+                for (int i = et; i < BLOCK_N; i += 32 * EPI_WARPS) {
+                    st_shared_f32(s_affine_addr + (uint32_t)(tsel * 2 * BLOCK_N + i) * 4u, p.scale[n_tile * BLOCK_N + i]);
+                    st_shared_f32(s_affine_addr + (uint32_t)(tsel * 2 * BLOCK_N + BLOCK_N + i) * 4u, p.shift[n_tile * BLOCK_N + i]);
+                }
+                asm volatile("bar.sync 1, %0;" :: "n"(32 * EPI_WARPS) : "memory");
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const uint32_t sa_addr = s_affine_addr + (uint32_t)(tsel * 2 * BLOCK_N) * 4u;
 
             const size_t opix = (size_t)((size_t)nn * oh + oy) * ow + ox;
             float* orow_f = reinterpret_cast<float*>(p.dst) + opix * p.dst_ld + p.dst_c_off + n_tile * BLOCK_N;
 
             // affine + activation + store of 32 consecutive output channels held as fp32 in v[]
             auto finish = [&](int c, const float* v) {
+                float sc[32], sh[32];                // this group's scale / shift
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    ld_shared_f32x4(sa_addr + (uint32_t)(c * 32 + 4 * j) * 4u, &sc[4 * j]);
+                    ld_shared_f32x4(sa_addr + (uint32_t)(BLOCK_N + c * 32 + 4 * j) * 4u, &sh[4 * j]);
+                }
                 if (p.out_f32) {                     // dgrad: fp32 NHWC destination
                     if (valid) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             uint32_t o8[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e)
-                                o8[e] = __float_as_uint(fmaf(v[8 * j + e], sa[c * 32 + 8 * j + e], sa[BLOCK_N + c * 32 + 8 * j + e]));
+                            for (int e = 0; e < 8; ++e) o8[e] = __float_as_uint(fmaf(v[8 * j + e], sc[8 * j + e], sh[8 * j + e]));
                             st_global_32B(orow_f + c * 32 + 8 * j, o8);
                         }
                     }
@@ -468,8 +488,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                 float a[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const int col = c * 32 + j;
-                    float t = fmaf(v[j], sa[col], sa[BLOCK_N + col]);
+                    float t = fmaf(v[j], sc[j], sh[j]);
                     if (p.relu) t = fmaxf(t, 0.0f);
                     a[j] = fminf(fmaxf(t, -65504.0f), 65504.0f);
                 }
@@ -555,7 +574,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS);
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                for (int c = cg0; c < BLOCK_N / 32; c += EPI_SPLIT) {
                     float v[32];
                     load_group(t_row, c, v);
                     finish(c, v);
@@ -564,24 +583,29 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             } else {
                 // long reductions: every K chunk is summed inside TMEM (truncating accumulator), the chunks are summed here
                 // in fp32 round-to-nearest -- error grows with sqrt(chunks) instead of linearly with K
-                float racc[BLOCK_N];
+                constexpr int MY_GROUPS = (BLOCK_N / 32 + EPI_SPLIT - 1) / EPI_SPLIT;       // column groups cg0, cg0 + EPI_SPLIT, ...
+                float racc[MY_GROUPS * 32];
 #pragma unroll
-                for (int j = 0; j < BLOCK_N; ++j) racc[j] = 0.0f;
+                for (int j = 0; j < MY_GROUPS * 32; ++j) racc[j] = 0.0f;
                 for (int ch = 0; ch < n_chunks; ++ch) {
                     mbar_wait(&tfull_bar[acc], acc_phase);
                     tc_fence_after();
                     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS);
 #pragma unroll
-                    for (int c = 0; c < BLOCK_N / 32; ++c) {
-                        float v[32];
-                        load_group(t_row, c, v);
+                    for (int g = 0; g < MY_GROUPS; ++g) {
+                        const int c = cg0 + g * EPI_SPLIT;
+                        if (c < BLOCK_N / 32) {
+                            float v[32];
+                            load_group(t_row, c, v);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) racc[c * 32 + j] += v[j];
+                            for (int j = 0; j < 32; ++j) racc[g * 32 + j] += v[j];
+                        }
                     }
                     release();
                 }
 #pragma unroll
-                for (int c = 0; c < BLOCK_N / 32; ++c) finish(c, &racc[c * 32]);
+                for (int g = 0; g < MY_GROUPS; ++g)
+                    if (cg0 + g * EPI_SPLIT < BLOCK_N / 32) finish(cg0 + g * EPI_SPLIT, &racc[g * 32]);
             }
         }
     }

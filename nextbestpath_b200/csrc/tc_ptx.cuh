@@ -206,6 +206,10 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* v) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void ld_shared_f32x4(uint32_t addr, float* v) {
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
 // One 32-byte global store per thread (STG.256, sm_100+): a full L2 sector per request.  `ptr` must be 32-byte aligned.
 __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t* r) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
