@@ -155,7 +155,9 @@ typedef struct nbp_conv_desc {
     int c_out;                             /* multiple of 32 */
     const float* scale; const float* shift;/* [c_out] fp32: y = acc*scale + shift */
     int relu;
-    void* dst; int dst_ld; int dst_c_off;  /* NHWC fp16 output, written at channels [dst_c_off, dst_c_off+c_out) */
+    void* dst; int dst_ld; int dst_c_off;  /* NHWC fp16 output, written at channels [dst_c_off, dst_c_off+c_out).  The epilogue stores 32-byte
+                                              pieces: dst and pool_dst 32-byte aligned; dst_ld, dst_c_off, dst_lo_off, pool_ld, pool_lo_off
+                                              multiples of 16 (fp32 output: dst_ld, dst_c_off multiples of 8) */
     int dst_lo_off;                        /* precise: lo plane written dst_lo_off elements after the hi channels */
     int out_f32;                           /* 1: dst is plain fp32 NHWC [pix][dst_ld] (used for dgrad: gradients are fp32) */
     int k_chunk;                           /* precise mode: number of 64-element K slices summed inside the tensor core's (truncating)

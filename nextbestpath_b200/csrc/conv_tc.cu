@@ -73,7 +73,24 @@ static constexpr int CONV_THREADS = 64 + 32 * EPI_WARPS;
 static constexpr int SMEM_LIMIT = 232448;                  // 227 KB opt-in maximum per CTA
 static constexpr int SMEM_AUX = 4096;                      // barriers + tmem ptr + scale/shift staging
 
+// n / d and n % d for 0 <= n < 2^31 by one multiply-high (Granlund-Montgomery round-up multiplier)
+struct FastDiv { uint32_t d, mul, shr; };
+static FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f{d, 0u, 0u};
+    if (d <= 1) return f;
+    uint32_t lg = 0;
+    while ((1ull << lg) < d) ++lg;
+    f.mul = (uint32_t)(((1ull << (31 + lg)) + d - 1) / d);
+    f.shr = lg - 1;
+    return f;
+}
+__device__ __forceinline__ void fast_divmod(const FastDiv& f, int n, int& q, int& r) {
+    q = f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr);
+    r = n - q * (int)f.d;
+}
+
 struct ConvKParams {
+    FastDiv fd_n_tiles, fd_tiles_x, fd_tiles_y;   // tile index -> (n-tile, x, y, image group)
     int n, h, w;
     int tw, th, tn, tiles_x, tiles_y, tiles_n;
     int m_tiles, n_tiles;
@@ -210,13 +227,14 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                 }
             };
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-                const int parity = tile / tiles_per_parity;              // 0 unless up2x: (py, px) = (parity >> 1, parity & 1)
-                const int tpl = tile - parity * tiles_per_parity;
-                const int n_tile = tpl % p.n_tiles;
-                int mt = min((tpl / p.n_tiles) * CL + (int)crank, p.m_tiles - 1);
-                const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-                const int ty = mt % p.tiles_y;
-                const int tb = mt / p.tiles_y;
+                // parities of one m-tile are adjacent work items (concurrent CTAs): the A block comes from DRAM once, not once per parity sweep
+                const int parity = p.up2x ? (tile & 3) : 0;              // (py, px) = (parity >> 1, parity & 1)
+                const int tpl = p.up2x ? (tile >> 2) : tile;
+                int n_tile, mt, tx, ty, tb;
+                fast_divmod(p.fd_n_tiles, tpl, mt, n_tile);
+                mt = min(mt * CL + (int)crank, p.m_tiles - 1);
+                fast_divmod(p.fd_tiles_x, mt, mt, tx);
+                fast_divmod(p.fd_tiles_y, mt, tb, ty);
                 const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tb * p.tn;
                 const int b_row0 = parity * p.b_rows_per_parity + n_tile * Cfg::NTILE_ROWS;
                 for (int g = 0; g < p.ngroups; ++g) {
@@ -309,7 +327,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                     if (HALO) {
                         // tap j of the column reads the SAME A block from tile row (row0 + j): a multiple of 8 pixel rows = 1024 B,
                         // so the swizzle phase is unchanged and only the descriptor address moves
-                        const int row0 = p.up2x ? ((tile / tiles_per_parity) >> 1) : 0;
+                        const int row0 = p.up2x ? ((tile & 3) >> 1) : 0;
 #pragma unroll
                         for (int j = 0; j < HALO; ++j) {
                             const uint64_t adesc = umma_desc_kmajor_sw128(a_addr + (uint32_t)((row0 + j) * p.aoff_step));
@@ -433,15 +451,15 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         int tsel = 0;
         const int n_chunks = (num_k + p.kchunk - 1) / p.kchunk;
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-            const int parity = tile / tiles_per_parity;
-            const int tpl = tile - parity * tiles_per_parity;
-            const int n_tile = tpl % p.n_tiles;
-            int mt = (tpl / p.n_tiles) * CL + (int)crank;
+            const int parity = p.up2x ? (tile & 3) : 0;
+            const int tpl = p.up2x ? (tile >> 2) : tile;
+            int n_tile, mt, tx, ty, tb;
+            fast_divmod(p.fd_n_tiles, tpl, mt, n_tile);
+            mt = mt * CL + (int)crank;
             const bool ghost = mt >= p.m_tiles;
             mt = min(mt, p.m_tiles - 1);
-            const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-            const int ty = mt % p.tiles_y;
-            const int tb = mt / p.tiles_y;
+            fast_divmod(p.fd_tiles_x, mt, mt, tx);
+            fast_divmod(p.fd_tiles_y, mt, tb, ty);
             const int wi = m % p.tw, hi = (m / p.tw) % p.th, ni = m / (p.tw * p.th);
             const int x = tx * p.tw + wi, y = ty * p.th + hi, nn = tb * p.tn + ni;
             const bool valid = x < p.w && y < p.h && nn < p.n && !ghost;
@@ -466,6 +484,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             float* orow_f = reinterpret_cast<float*>(p.dst) + opix * p.dst_ld + p.dst_c_off + n_tile * BLOCK_N;
 
             // affine + activation + store of 32 consecutive output channels held as fp32 in v[]
+            const float lower = p.relu ? 0.0f : -65504.0f;
             auto finish = [&](int c, const float* v) {
                 float sc[32], sh[32];                // this group's scale / shift
 #pragma unroll
@@ -480,7 +499,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                             uint32_t o8[8];
 #pragma unroll
                             for (int e = 0; e < 8; ++e) o8[e] = __float_as_uint(fmaf(v[8 * j + e], sc[8 * j + e], sh[8 * j + e]));
-                            st_global_32B(orow_f + c * 32 + 8 * j, o8);
+                            st_global_v8(orow_f + c * 32 + 8 * j, o8);
                         }
                     }
                     return;
@@ -488,9 +507,7 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                 float a[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    float t = fmaf(v[j], sc[j], sh[j]);
-                    if (p.relu) t = fmaxf(t, 0.0f);
-                    a[j] = fminf(fmaxf(t, -65504.0f), 65504.0f);
+                    a[j] = fminf(fmaxf(fmaf(v[j], sc[j], sh[j]), lower), 65504.0f);      // ReLU (lower = 0) and the fp16 range clamp in one
                 }
                 // fp32 -> hi plane (fp16) + second plane -> 16-byte stores.  `pix` = first element of the pixel, `ch` = channel of x[0]
                 // inside the pixel, `lo_off` = offset of the second plane; fmt 1: fp16 (x - hi) * 2048 at the same channel index,
@@ -511,9 +528,9 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                             sat |= fmaxf(fabsf(x[2 * j]), fabsf(x[2 * j + 1])) > NBP_E4M3_MAX / NBP_E4M3_ACT_SCALE;
                             if (j & 1) { p8h[j >> 1] |= qh << 16; p8l[j >> 1] |= ql << 16; } else { p8h[j >> 1] = qh; p8l[j >> 1] = ql; }
                         }
-                        st_global_32B(pix + ch, packed); st_global_32B(pix + ch + 16, packed + 8);
+                        st_global_v8(pix + ch, packed); st_global_v8(pix + ch + 16, packed + 8);
                         uint8_t* g = reinterpret_cast<uint8_t*>(pix + lo_off) + (ch >> 6) * 128 + (ch & 63);
-                        st_global_32B(g, p8h); st_global_32B(g + 64, p8l);
+                        st_global_v8(g, p8h); st_global_v8(g + 64, p8l);
                         if (sat && p.sat_count) atomicAdd(p.sat_count, 1ull);          // rare by construction: out-of-range inputs only
                         return;
                     }
@@ -528,8 +545,8 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                             packed_lo[j] = *reinterpret_cast<const uint32_t*>(&l);
                         }
                     }
-                    st_global_32B(pix + ch, packed); st_global_32B(pix + ch + 16, packed + 8);
-                    if (PRECISE) { st_global_32B(pix + ch + lo_off, packed_lo); st_global_32B(pix + ch + lo_off + 16, packed_lo + 8); }
+                    st_global_v8(pix + ch, packed); st_global_v8(pix + ch + 16, packed + 8);
+                    if (PRECISE) { st_global_v8(pix + ch + lo_off, packed_lo); st_global_v8(pix + ch + lo_off + 16, packed_lo + 8); }
                 };
                 if (valid) split_store(p.dst + opix * p.dst_ld, p.dst_c_off + n_tile * BLOCK_N + c * 32, p.dst_lo_off, p.dst_fmt, a);
                 if (p.pool) {
@@ -760,8 +777,15 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     if (d->c_out <= 0 || d->c_out % 32) return invalid("nbp_conv_fwd: c_out must be a positive multiple of 32 (got %d)", d->c_out);
     if (d->dst_ld % 8 || d->dst_c_off % 8 || d->dst_c_off + ((precise && !d->out_f32) ? d->dst_lo_off : 0) + d->c_out > d->dst_ld)
         return invalid("nbp_conv_fwd: bad destination channel layout ld=%d off=%d lo_off=%d c_out=%d", d->dst_ld, d->dst_c_off, d->dst_lo_off, d->c_out);
-    if (((uintptr_t)d->src0 | (uintptr_t)d->src1 | (uintptr_t)d->weight | (uintptr_t)d->dst) & 15)
-        return invalid("nbp_conv_fwd: pointers must be 16-byte aligned");
+    if (((uintptr_t)d->src0 | (uintptr_t)d->src1 | (uintptr_t)d->weight) & 15)
+        return invalid("nbp_conv_fwd: source and weight pointers must be 16-byte aligned");
+    // the epilogue writes 32-byte pieces (16 fp16 channels / 8 fp32 values / 32 e4m3 bytes per store)
+    if (((uintptr_t)d->dst | (uintptr_t)d->pool_dst) & 31) return invalid("nbp_conv_fwd: destination pointers must be 32-byte aligned");
+    if (!d->out_f32 && (d->dst_ld % 16 || d->dst_c_off % 16 || (precise && d->dst_lo_off % 16)))
+        return invalid("nbp_conv_fwd: fp16 destinations need ld, channel offset and plane offset in multiples of 16 (ld=%d off=%d lo_off=%d)",
+                       d->dst_ld, d->dst_c_off, d->dst_lo_off);
+    if (d->pool_dst && (d->pool_ld % 16 || (precise && d->pool_lo_off % 16)))
+        return invalid("nbp_conv_fwd: the pooled destination needs ld and plane offset in multiples of 16 (ld=%d lo_off=%d)", d->pool_ld, d->pool_lo_off);
 
     const int block_n = (d->c_out % 128 == 0) ? 128 : (d->c_out % 64 == 0) ? 64 : 32;
     ConvKParams kp{};
@@ -772,6 +796,7 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     kp.tn = BLOCK_M / (kp.tw * kp.th);
     kp.tiles_x = (d->w + kp.tw - 1) / kp.tw; kp.tiles_y = (d->h + kp.th - 1) / kp.th; kp.tiles_n = (d->n + kp.tn - 1) / kp.tn;
     kp.m_tiles = kp.tiles_x * kp.tiles_y * kp.tiles_n; kp.n_tiles = d->c_out / block_n;
+    kp.fd_n_tiles = make_fastdiv((uint32_t)kp.n_tiles); kp.fd_tiles_x = make_fastdiv((uint32_t)kp.tiles_x); kp.fd_tiles_y = make_fastdiv((uint32_t)kp.tiles_y);
     kp.taps = d->taps; kp.kc0 = d->c0 / BLOCK_K; kp.kc1 = d->c1 / BLOCK_K;
     kp.lo0 = d->lo0; kp.lo1 = d->lo1;
     kp.lo_scale = fp8 ? d->w_lo_scale / NBP_E4M3_ACT_SCALE : 1.0f / 2048.0f;

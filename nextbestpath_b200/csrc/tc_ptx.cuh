@@ -215,14 +215,6 @@ __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t* r) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  :: "l"(ptr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
-// 8 consecutive 32-bit words to `ptr`: one 32-byte store when the address allows it, else two 16-byte stores
-__device__ __forceinline__ void st_global_32B(void* ptr, const uint32_t* r) {
-    if ((reinterpret_cast<uintptr_t>(ptr) & 31u) == 0) st_global_v8(ptr, r);
-    else {
-        uint4* o = reinterpret_cast<uint4*>(ptr);
-        o[0] = make_uint4(r[0], r[1], r[2], r[3]); o[1] = make_uint4(r[4], r[5], r[6], r[7]);
-    }
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------ descriptors
