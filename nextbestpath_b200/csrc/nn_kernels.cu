@@ -86,12 +86,16 @@ __device__ __forceinline__ void store8(__half* pix, int ch, int lo, int fmt, con
 // instruction; an 8-lanes-per-pixel variant fixed the stores but multiplied the input loads by 8 and was 2.5x slower).
 static constexpr int CF_ROW = 68;                 // floats per staged pixel row (64 + 4: 16-byte aligned, conflict-free float4 columns)
 
-template <int COUT>
-__global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict__ x, int n, int cin, int h, int w,
+// CIN > 0: compile-time input channels (5 = the NBP model input); CIN = 0: run-time `cin` (one tap per load batch)
+template <int COUT, int CIN>
+__global__ void __launch_bounds__(128, 4) conv_first_kernel(const float* __restrict__ x, int n, int cin_rt, int h, int w,
                                                          const float* __restrict__ wt,      // [9*cin][COUT]
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                                          __half* __restrict__ dst, int dst_ld, int dst_lo, int relu, int fmt) {
     static_assert(COUT == 64, "the staging tile is 64 channels wide");
+    const int cin = CIN > 0 ? CIN : cin_rt;
+    constexpr int CMAX = CIN > 0 ? CIN : 16;          // nbp_conv_first admits c_in <= 16
+    constexpr int TXB = CIN > 0 ? 3 : 1;              // taps per load batch
     extern __shared__ float s_w[];                    // 9*cin*COUT weights, scale, shift, then 4 warps x 32 x CF_ROW staging
     const int nw = 9 * cin * COUT;
     for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = wt[i];
@@ -113,20 +117,38 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict
 #pragma unroll
             for (int c = 0; c < COUT; ++c) acc[c] = 0.0f;
             const float* xin = x + (size_t)img * cin * hw;
-            for (int tap = 0; tap < 9; ++tap) {
-                const int yy = y + tap / 3 - 1, xc = xx + tap % 3 - 1;
-                if (yy < 0 || yy >= h || xc < 0 || xc >= w) continue;
-                for (int ci = 0; ci < cin; ++ci) {
-                    const float v = __ldg(xin + (size_t)ci * hw + (size_t)yy * w + xc);
-                    if (v == 0.0f) continue;                         // count images are sparse
-                    const float4* wr = reinterpret_cast<const float4*>(s_w + (tap * cin + ci) * COUT);
+            // TXB taps of one row at a time: their input values are loaded back to back (one exposed load latency per batch, not per
+            // value: the kernel was bound by 45 dependent load -> FMA steps per pixel)
+#pragma unroll 1
+            for (int tb = 0; tb < 9; tb += TXB) {
+                const int ty = tb / 3, tx0 = tb - 3 * ty;
+                const int yy = y + ty - 1;
+                const bool row_in = yy >= 0 && yy < h;
+                const float* row = xin + (size_t)(row_in ? yy : 0) * w;
+                float v[TXB][CMAX];
 #pragma unroll
-                    for (int c4 = 0; c4 < COUT / 4; ++c4) {
-                        const float4 q = wr[c4];
-                        acc[4 * c4 + 0] = fmaf(v, q.x, acc[4 * c4 + 0]);
-                        acc[4 * c4 + 1] = fmaf(v, q.y, acc[4 * c4 + 1]);
-                        acc[4 * c4 + 2] = fmaf(v, q.z, acc[4 * c4 + 2]);
-                        acc[4 * c4 + 3] = fmaf(v, q.w, acc[4 * c4 + 3]);
+                for (int t = 0; t < TXB; ++t) {
+                    const int xc = xx + tx0 + t - 1;
+                    const bool in = row_in && xc >= 0 && xc < w;
+#pragma unroll
+                    for (int ci = 0; ci < CMAX; ++ci) v[t][ci] = (in && ci < cin) ? __ldg(row + (size_t)ci * hw + xc) : 0.0f;
+                }
+#pragma unroll
+                for (int t = 0; t < TXB; ++t) {
+#pragma unroll
+                    for (int ci = 0; ci < CMAX; ++ci) {
+                        if (ci >= cin) break;
+                        const float vv = v[t][ci];
+                        if (vv == 0.0f) continue;                         // count images are sparse
+                        const float4* wr = reinterpret_cast<const float4*>(s_w + ((tb + t) * cin + ci) * COUT);
+#pragma unroll
+                        for (int c4 = 0; c4 < COUT / 4; ++c4) {
+                            const float4 q = wr[c4];
+                            acc[4 * c4 + 0] = fmaf(vv, q.x, acc[4 * c4 + 0]);
+                            acc[4 * c4 + 1] = fmaf(vv, q.y, acc[4 * c4 + 1]);
+                            acc[4 * c4 + 2] = fmaf(vv, q.z, acc[4 * c4 + 2]);
+                            acc[4 * c4 + 3] = fmaf(vv, q.w, acc[4 * c4 + 3]);
+                        }
                     }
                 }
             }
@@ -312,8 +334,9 @@ extern "C" int nbp_conv_first(const float* x, int n, int c_in, int h, int w, con
     if (dst_lo >= 0 && (rc = check_fmt("nbp_conv_first", fmt, fmt == 2 ? dst_lo : 64))) return rc;
     const size_t smem = sizeof(float) * (size_t)(9 * c_in * 64 + 128 + 4 * 32 * CF_ROW);
     if (smem > 48 * 1024) return invalid("nbp_conv_first: c_in=%d needs more than 48 KB of shared memory", c_in);
-    conv_first_kernel<64><<<grid_for((size_t)n * h * w, 128), 128, smem, (cudaStream_t)stream>>>(x, n, c_in, h, w, weight, scale, shift,
-                                                                                                  (__half*)dst, dst_ld, dst_lo, relu, fmt);
+    const int g = grid_for((size_t)n * h * w, 128);
+    if (c_in == 5) conv_first_kernel<64, 5><<<g, 128, smem, (cudaStream_t)stream>>>(x, n, c_in, h, w, weight, scale, shift, (__half*)dst, dst_ld, dst_lo, relu, fmt);
+    else conv_first_kernel<64, 0><<<g, 128, smem, (cudaStream_t)stream>>>(x, n, c_in, h, w, weight, scale, shift, (__half*)dst, dst_ld, dst_lo, relu, fmt);
     count_launch();
     return check_cuda(cudaGetLastError(), "nbp_conv_first launch");
 }
