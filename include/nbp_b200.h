@@ -177,6 +177,14 @@ typedef struct nbp_conv_desc {
                                               as an NHWC fp16 tensor [n][h/2][w/2][pool_ld] (lo plane pool_lo_off elements after the hi
                                               channels), fused into the epilogue: the encoder needs both the skip tensor and its pooled
                                               copy.  h, w even; not with up2x / out_f32 */
+    const float* dot_w; float* dot_out;    /* optional (dot_out NULL = off) "dot" epilogue: the c_out activations of a pixel are NOT stored (dst may be
+                                              NULL) but contracted in fp32 with dot_w [c_out] (16-byte aligned):
+                                              dot_out[pixel] = f(dot_scale * sum_c y[c] * dot_w[c] + dot_shift), f = sigmoid if dot_sigmoid else
+                                              identity; dot_out fp32 [n][h][w] ([n][2h][2w] with up2x).  Fuses the 1-channel 1x1 convolution that
+                                              consumes this layer -- Attention_block.psi (nbp_model.py:49-53,60) and Final2 (:106-108) -- so the
+                                              layer's output never goes to memory.  c_out = 32, 64 or 128 (one n-tile); the whole K reduction
+                                              runs as one in-TMEM chain (k_chunk is ignored); not with out_f32 / pool_dst */
+    float dot_scale; float dot_shift; int dot_sigmoid;
 } nbp_conv_desc;
 
 /* tcgen05/TMEM/TMA implicit-GEMM convolution: conv_block / up_conv / Attention_block W_g,W_x (nbp_model.py:8-62) */
@@ -204,6 +212,10 @@ int nbp_upsample2x(const void* src, int n, int h, int w, int c, int ld_src, int 
 int nbp_att_gate(const void* a, int f_int, int ld_a, int lo_a, const void* x, int f_l, int ld_x, int lo_x,
                  const float* w_psi, float psi_scale, float psi_shift,
                  void* dst, int dst_ld, int dst_c_off, int dst_lo, int64_t npix, int fmt, void* stream);
+/* The same tail with psi [npix] fp32 already computed -- by the dot epilogue of the attention GEMM (nbp_conv_desc.dot_out):
+ * dst[:, dst_c_off : dst_c_off + f_l] = x * psi (nbp_model.py:62) */
+int nbp_att_scale(const float* psi, const void* x, int f_l, int ld_x, int lo_x,
+                  void* dst, int dst_ld, int dst_c_off, int dst_lo, int64_t npix, int fmt, void* stream);
 /* Final1 (256->8) and Final2 (64->1, sigmoid) (nbp_model.py:89,106-108): NHWC fp16 in, NCHW fp32 out [n,c_out,hw];
  * weight fp32 [c_out][c_in], c_out in {1, 8}.  dst_max (optional, NULL = off): [n,hw] fp32 = max over the c_out channels, the
  * heading read-out `torch.max(predicted_value_map, dim=1)` of next_best_path/testers/nbp_planning.py:193 fused into the head */

@@ -42,7 +42,8 @@ class ConvDesc(C.Structure):
                 ("n", _i), ("h", _i), ("w", _i), ("taps", _i), ("up2x", _i), ("weight", _p), ("c_out", _i),
                 ("scale", _p), ("shift", _p), ("relu", _i), ("dst", _p), ("dst_ld", _i), ("dst_c_off", _i),
                 ("dst_lo_off", _i), ("out_f32", _i), ("k_chunk", _i), ("dst_fmt", _i), ("pool_fmt", _i), ("w_lo_scale", _f),
-                ("sat_count", _p), ("pool_dst", _p), ("pool_ld", _i), ("pool_lo_off", _i)]
+                ("sat_count", _p), ("pool_dst", _p), ("pool_ld", _i), ("pool_lo_off", _i),
+                ("dot_w", _p), ("dot_out", _p), ("dot_scale", _f), ("dot_shift", _f), ("dot_sigmoid", _i)]
 
 
 SIGNATURES.update({
@@ -53,6 +54,7 @@ SIGNATURES.update({
     "nbp_maxpool2x2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     "nbp_upsample2x": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     "nbp_att_gate": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p, _f, _f, _p, _i, _i, _i, _l, _i, _p]),
+    "nbp_att_scale": (_i, [_p, _p, _i, _i, _i, _p, _i, _i, _i, _l, _i, _p]),
     "nbp_conv1x1_head": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _l, _i, _p]),
 })
 

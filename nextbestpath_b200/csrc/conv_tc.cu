@@ -116,6 +116,10 @@ struct ConvKParams {
     int relu;
     __half* dst; int dst_ld, dst_c_off, dst_lo_off;
     __half* pool; int pool_ld, pool_lo_off;   // optional second output: the 2x2 max-pooled activation [n][h/2][w/2] (fused nn.MaxPool2d)
+    // optional "dot" epilogue (n_tiles == 1, one accumulation chain): the activation tile is NOT stored; every pixel's c_out activations
+    // are contracted with dot_w in fp32 and dot_out[pixel] = f(dot * dot_scale + dot_shift), f = sigmoid or identity.  Fuses the 1-channel
+    // 1x1 convolution that follows (Attention_block.psi, Final2) so that its input never goes to memory.
+    const float* dot_w; float* dot_out; float dot_scale, dot_shift; int dot_sigmoid;
 };
 
 // MODE 0 fp16 | 1 fp16x2 | 2 fp16+e4m3 | 3 fp16+e4m3 with SPLIT stages; HALO = 0: plain stages; 2 | 3: halo stages carrying that many taps.
@@ -450,7 +454,13 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         int acc = 0; uint32_t acc_phase = 0;
         int tsel = 0;
         const int n_chunks = (num_k + p.kchunk - 1) / p.kchunk;
+        // dot epilogue: one thread contracts ALL column groups of its pixel (warps of the first column-group set; the others only keep
+        // the accumulator hand-shake going): the tile's values stay in registers, no stores, so four warps are plenty
+        const bool dotm = p.dot_out != nullptr;
+        const int c_step = dotm ? 1 : EPI_SPLIT;
+        const int c_end = (dotm && cg0 != 0) ? 0 : BLOCK_N / 32;
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+            float dot = 0.0f;
             const int parity = p.up2x ? (tile & 3) : 0;
             const int tpl = p.up2x ? (tile >> 2) : tile;
             int n_tile, mt, tx, ty, tb;
@@ -508,6 +518,16 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     a[j] = fminf(fmaxf(fmaf(v[j], sc[j], sh[j]), lower), 65504.0f);      // ReLU (lower = 0) and the fp16 range clamp in one
+                }
+                if (dotm) {                          // channels in ascending order, one fused multiply-add each: deterministic
+                    const float4* dw = reinterpret_cast<const float4*>(p.dot_w + n_tile * BLOCK_N + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 q = __ldg(dw + j);
+                        dot = fmaf(a[4 * j], q.x, dot); dot = fmaf(a[4 * j + 1], q.y, dot);
+                        dot = fmaf(a[4 * j + 2], q.z, dot); dot = fmaf(a[4 * j + 3], q.w, dot);
+                    }
+                    return;
                 }
                 // fp32 -> hi plane (fp16) + second plane -> 16-byte stores.  `pix` = first element of the pixel, `ch` = channel of x[0]
                 // inside the pixel, `lo_off` = offset of the second plane; fmt 1: fp16 (x - hi) * 2048 at the same channel index,
@@ -591,12 +611,17 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS);
 #pragma unroll 1
-                for (int c = cg0; c < BLOCK_N / 32; c += EPI_SPLIT) {
+                for (int c = cg0; c < c_end; c += c_step) {
                     float v[32];
                     load_group(t_row, c, v);
                     finish(c, v);
                 }
                 release();
+                if (dotm && cg0 == 0 && valid) {
+                    float z = fmaf(dot, p.dot_scale, p.dot_shift);
+                    if (p.dot_sigmoid) z = 1.0f / (1.0f + expf(-z));
+                    p.dot_out[opix] = z;
+                }
             } else {
                 // long reductions: every K chunk is summed inside TMEM (truncating accumulator), the chunks are summed here
                 // in fp32 round-to-nearest -- error grows with sqrt(chunks) instead of linearly with K
@@ -752,7 +777,10 @@ using namespace nbp;
 
 extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     if (!d) return invalid("nbp_conv_fwd: null descriptor");
-    if (!d->src0 || !d->weight || !d->scale || !d->shift || !d->dst) return invalid("nbp_conv_fwd: null pointer in descriptor");
+    const bool dotm = d->dot_out != nullptr;
+    if (!d->src0 || !d->weight || !d->scale || !d->shift || (!d->dst && !dotm)) return invalid("nbp_conv_fwd: null pointer in descriptor");
+    if (dotm && (!d->dot_w || d->out_f32 || d->pool_dst || (d->c_out != 32 && d->c_out != 64 && d->c_out != 128) || ((uintptr_t)d->dot_w & 15)))
+        return invalid("nbp_conv_fwd: the dot epilogue needs dot_w (16-byte aligned), c_out = 32, 64 or 128 (one n-tile; got %d), no fp32 / pooled output", d->c_out);
     if (d->taps != 1 && d->taps != 9 && !(d->taps == 4 && d->up2x)) return invalid("nbp_conv_fwd: taps must be 1 or 9, or 4 with up2x (got %d)", d->taps);
     if (d->up2x && d->taps != 4) return invalid("nbp_conv_fwd: up2x needs the 4-tap parity weights");
     if (d->n <= 0 || d->h <= 0 || d->w <= 0) return invalid("nbp_conv_fwd: bad image dims n=%d h=%d w=%d", d->n, d->h, d->w);
@@ -764,24 +792,24 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     if (fp8 && d->out_f32) return invalid("nbp_conv_fwd: the fp16+e4m3 mode has no fp32 output (it is an eval-path format)");
     if (fp8 && !(d->w_lo_scale > 0.0f)) return invalid("nbp_conv_fwd: precise = 2 needs w_lo_scale = 1 / (2048 s) > 0");
     const int dst_fmt = d->dst_fmt ? d->dst_fmt : d->precise, pool_fmt = d->pool_fmt ? d->pool_fmt : d->precise;   // 0 = the mode's own format
-    if (precise && !d->out_f32 && dst_fmt != 1 && dst_fmt != 2) return invalid("nbp_conv_fwd: dst_fmt must be 0 (as the sources), 1 (fp16 lo plane) or 2 (e4m3 pair plane)");
+    if (!dotm && precise && !d->out_f32 && dst_fmt != 1 && dst_fmt != 2) return invalid("nbp_conv_fwd: dst_fmt must be 0 (as the sources), 1 (fp16 lo plane) or 2 (e4m3 pair plane)");
     if (precise && d->pool_dst && pool_fmt != 1 && pool_fmt != 2) return invalid("nbp_conv_fwd: pool_fmt must be 0, 1 or 2");
-    if (precise && ((dst_fmt == 2 && (d->dst_c_off % 32 || d->dst_lo_off % 64)) || (d->pool_dst && pool_fmt == 2 && d->pool_lo_off % 64)))
+    if (precise && ((!dotm && dst_fmt == 2 && (d->dst_c_off % 32 || d->dst_lo_off % 64)) || (d->pool_dst && pool_fmt == 2 && d->pool_lo_off % 64)))
         return invalid("nbp_conv_fwd: e4m3 pair planes need 64-channel aligned plane offsets");
     const int span0 = precise ? d->lo0 + d->c0 : d->c0, span1 = precise ? d->lo1 + d->c1 : d->c1;
     if (precise && (d->lo0 < d->c0 || d->lo0 % 8 || (d->c1 > 0 && (d->lo1 < d->c1 || d->lo1 % 8)) ||
-                    (!d->out_f32 && (d->dst_lo_off < d->c_out || d->dst_lo_off % 8))))
+                    (!d->out_f32 && !dotm && (d->dst_lo_off < d->c_out || d->dst_lo_off % 8))))
         return invalid("nbp_conv_fwd: lo-plane offsets must be >= the channel count and multiples of 8");
     if (d->ld0 < span0 || d->ld0 % 8 || (d->c1 > 0 && (d->ld1 < span1 || d->ld1 % 8)))
         return invalid("nbp_conv_fwd: source pixel strides must cover the planes and be multiples of 8");
     if (d->c_out <= 0 || d->c_out % 32) return invalid("nbp_conv_fwd: c_out must be a positive multiple of 32 (got %d)", d->c_out);
-    if (d->dst_ld % 8 || d->dst_c_off % 8 || d->dst_c_off + ((precise && !d->out_f32) ? d->dst_lo_off : 0) + d->c_out > d->dst_ld)
+    if (!dotm && (d->dst_ld % 8 || d->dst_c_off % 8 || d->dst_c_off + ((precise && !d->out_f32) ? d->dst_lo_off : 0) + d->c_out > d->dst_ld))
         return invalid("nbp_conv_fwd: bad destination channel layout ld=%d off=%d lo_off=%d c_out=%d", d->dst_ld, d->dst_c_off, d->dst_lo_off, d->c_out);
     if (((uintptr_t)d->src0 | (uintptr_t)d->src1 | (uintptr_t)d->weight) & 15)
         return invalid("nbp_conv_fwd: source and weight pointers must be 16-byte aligned");
     // the epilogue writes 32-byte pieces (16 fp16 channels / 8 fp32 values / 32 e4m3 bytes per store)
     if (((uintptr_t)d->dst | (uintptr_t)d->pool_dst) & 31) return invalid("nbp_conv_fwd: destination pointers must be 32-byte aligned");
-    if (!d->out_f32 && (d->dst_ld % 16 || d->dst_c_off % 16 || (precise && d->dst_lo_off % 16)))
+    if (!dotm && !d->out_f32 && (d->dst_ld % 16 || d->dst_c_off % 16 || (precise && d->dst_lo_off % 16)))
         return invalid("nbp_conv_fwd: fp16 destinations need ld, channel offset and plane offset in multiples of 16 (ld=%d off=%d lo_off=%d)",
                        d->dst_ld, d->dst_c_off, d->dst_lo_off);
     if (d->pool_dst && (d->pool_ld % 16 || (precise && d->pool_lo_off % 16)))
@@ -844,11 +872,13 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
         // 8 + 1 makes the epilogue warps fold two chunks per tile for nothing (measured -3..-13 % on those layers); spreading
         // longer reductions evenly (18 as 6+6+6 instead of 8+8+2) was measured slower and is not done.
         if (precise && want > 0 && total > kp.kchunk && total / smult * kp.gtaps <= want + want / 4) kp.kchunk = total;
+        if (dotm) kp.kchunk = total;              // the dot epilogue contracts one whole accumulator per tile
     }
     kp.b_rows_per_parity = (precise ? 2 : 1) * d->c_out;
     kp.scale = d->scale; kp.shift = d->shift; kp.relu = d->relu;
     kp.dst = (__half*)d->dst; kp.dst_ld = d->dst_ld; kp.dst_c_off = d->dst_c_off; kp.dst_lo_off = d->dst_lo_off;
     kp.pool = (__half*)d->pool_dst; kp.pool_ld = d->pool_ld; kp.pool_lo_off = d->pool_lo_off;
+    kp.dot_w = d->dot_w; kp.dot_out = d->dot_out; kp.dot_scale = d->dot_scale; kp.dot_shift = d->dot_shift; kp.dot_sigmoid = d->dot_sigmoid ? 1 : 0;
     if (d->pool_dst) {
         if (d->up2x || d->out_f32) return invalid("nbp_conv_fwd: pool_dst cannot be combined with up2x / out_f32");
         if ((d->h | d->w) & 1) return invalid("nbp_conv_fwd: pool_dst needs even h and w (got %d x %d)", d->h, d->w);

@@ -8,6 +8,8 @@
 // All are HBM-bound streaming kernels: 16-byte vector accesses, one pass over their inputs.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "nbp_common.cuh"
 
 namespace nbp {
@@ -182,6 +184,122 @@ __global__ void __launch_bounds__(128, 4) conv_first_kernel(const float* __restr
     }
 }
 
+// The NBP stem itself (5 input channels, even image width): the generic kernel above is bound by FFMA issue (45 x 64 FFMA per pixel at
+// one 3-register FFMA per two clocks and scheduler) and, behind that, by its 16 LDS.128 of weights per 64 FFMA.  Here a thread owns TWO
+// horizontally adjacent pixels x 32 output channels (lanes 0-15: channels 0-31, lanes 16-31: channels 32-63 of the same 32 pixels):
+// every weight float4 feeds four packed fp32x2 FMAs (`fma.rn.f32x2`, two channels per instruction), i.e. 8 LDS.128 + 32 FFMA2 per
+// (tap, input channel) and pixel pair -- a quarter of the issue slots per pixel.  Every output channel still sums its 45 products in
+// the same order with one fused multiply-add each, so the results are bit-identical to the generic kernel's.
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
+// shared-memory position of output channel c inside a 64-float weight row: the float4 k of channels 0-31 sits next to the float4 k of
+// channels 32-63, so the two half-warps' broadcast reads of one LDS.128 fall into one 32-byte piece (no bank conflict)
+__device__ __forceinline__ int stem_wpos(int c) { return ((c & 31) >> 2) * 8 + (c >> 5) * 4 + (c & 3); }
+
+__global__ void __launch_bounds__(128, 4) conv_first5_kernel(const float* __restrict__ x, int n, int h, int w,
+                                                            const float* __restrict__ wt,      // [45][64]
+                                                            const float* __restrict__ scale, const float* __restrict__ shift,
+                                                            __half* __restrict__ dst, int dst_ld, int dst_lo, int relu, int fmt) {
+    constexpr int COUT = 64, CIN = 5;
+    extern __shared__ float s_w[];                    // 45 x 64 weights (channel-permuted rows), scale, shift, then 4 warps x 32 x CF_ROW staging
+    constexpr int nw = 9 * CIN * COUT;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[(i & ~63) + stem_wpos(i & 63)] = wt[i];
+    float* s_sc = s_w + nw; float* s_sh = s_sc + COUT;
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) { s_sc[i] = scale[i]; s_sh[i] = shift[i]; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pr = lane & 15, half = lane >> 4;       // pixel pair of the warp's 32 pixels, channel half
+    float* tile = s_sh + COUT + warp * 32 * CF_ROW;
+    __syncthreads();
+    const size_t hw = (size_t)h * w;
+    const size_t total = (size_t)n * hw;              // even (w is)
+    const size_t warp_stride = (size_t)gridDim.x * (blockDim.x >> 5) * 32;
+    for (size_t base = ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32; base < total; base += warp_stride) {
+        const size_t pix = base + 2 * pr;             // even pixel index -> even column, its right neighbour is in the same row
+        if (pix < total) {
+            const int img = (int)(pix / hw);
+            const int rem = (int)(pix - (size_t)img * hw);
+            const int y = rem / w, xx = rem - y * w;
+            unsigned long long acc0[COUT / 4], acc1[COUT / 4];      // [pixel][16 channel pairs of this half]
+#pragma unroll
+            for (int c = 0; c < COUT / 4; ++c) { acc0[c] = 0ull; acc1[c] = 0ull; }
+            const float* xin = x + (size_t)img * CIN * hw;
+            const bool left = xx > 0, right = xx + 2 < w;
+#pragma unroll 1
+            for (int ty = 0; ty < 3; ++ty) {
+                const int yy = y + ty - 1;
+                if (yy < 0 || yy >= h) continue;                   // a padding row contributes exact zeros
+                const float* row = xin + (size_t)yy * w + xx;
+                float v[CIN][4];                                     // columns xx-1 .. xx+2 of the 5 input channels, loaded back to back
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) {
+                    const float* q = row + (size_t)ci * hw;
+                    v[ci][0] = left ? __ldg(q - 1) : 0.0f;
+                    v[ci][1] = __ldg(q); v[ci][2] = __ldg(q + 1);
+                    v[ci][3] = right ? __ldg(q + 2) : 0.0f;
+                }
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+#pragma unroll
+                    for (int ci = 0; ci < CIN; ++ci) {
+                        const float v0 = v[ci][t], v1 = v[ci][t + 1];
+                        if (v0 == 0.0f && v1 == 0.0f) continue;       // count images are sparse
+                        const unsigned long long a0 = pack_f32x2(v0, v0), a1 = pack_f32x2(v1, v1);
+                        const float4* wr = reinterpret_cast<const float4*>(s_w + ((ty * 3 + t) * CIN + ci) * COUT) + half;
+#pragma unroll
+                        for (int c4 = 0; c4 < COUT / 8; ++c4) {
+                            const float4 q = wr[2 * c4];
+                            const unsigned long long w01 = pack_f32x2(q.x, q.y), w23 = pack_f32x2(q.z, q.w);
+                            ffma2(acc0[2 * c4], a0, w01); ffma2(acc0[2 * c4 + 1], a0, w23);
+                            ffma2(acc1[2 * c4], a1, w01); ffma2(acc1[2 * c4 + 1], a1, w23);
+                        }
+                    }
+                }
+            }
+            const float* sc = s_sc + half * 32; const float* sh = s_sh + half * 32;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+#pragma unroll
+                for (int c4 = 0; c4 < COUT / 8; ++c4) {
+                    float a[4];
+                    unpack_f32x2(k ? acc1[2 * c4] : acc0[2 * c4], a[0], a[1]);
+                    unpack_f32x2(k ? acc1[2 * c4 + 1] : acc0[2 * c4 + 1], a[2], a[3]);
+                    float4 o;
+                    o.x = fmaf(a[0], sc[4 * c4 + 0], sh[4 * c4 + 0]); o.y = fmaf(a[1], sc[4 * c4 + 1], sh[4 * c4 + 1]);
+                    o.z = fmaf(a[2], sc[4 * c4 + 2], sh[4 * c4 + 2]); o.w = fmaf(a[3], sc[4 * c4 + 3], sh[4 * c4 + 3]);
+                    if (relu) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
+                    *reinterpret_cast<float4*>(tile + (2 * pr + k) * CF_ROW + half * 32 + 4 * c4) = o;
+                }
+            }
+        }
+        __syncwarp();
+        // 8 lanes per pixel, 4 pixels per pass: lane -> (pixel 4*it + lane/8, channel octet lane%8)
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int pl = 4 * it + (lane >> 3), c8 = lane & 7;
+            const size_t pp = base + pl;
+            if (pp < total) {
+                const float4 a = *reinterpret_cast<const float4*>(tile + pl * CF_ROW + 8 * c8), b = *reinterpret_cast<const float4*>(tile + pl * CF_ROW + 8 * c8 + 4);
+                const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                if (dst_lo < 0) {                     // plain fp32 destination (train mode: the raw pre-BatchNorm tensor), row stride dst_ld floats
+                    float4* of = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + pp * dst_ld + 8 * c8);
+                    of[0] = a; of[1] = b;
+                } else {
+                    store8(dst + pp * dst_ld, 8 * c8, dst_lo, fmt, f);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ pool / upsample
 __global__ void __launch_bounds__(256) maxpool2x2_kernel(const __half* __restrict__ src, int n, int h, int w, int c, int ld_src, int lo_src,
                                                          __half* __restrict__ dst, int ld_dst, int lo_dst) {
@@ -222,7 +340,8 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __half* __restric
 __global__ void __launch_bounds__(256) att_gate_kernel(const __half* __restrict__ a, int f_int, int ld_a, int lo_a,
                                                        const __half* __restrict__ x, int f_l, int ld_x, int lo_x,
                                                        const float* __restrict__ w_psi, float psi_scale, float psi_shift,
-                                                       __half* __restrict__ dst, int ld_dst, int c_off, int lo_dst, size_t npix, int gs, int fmt) {
+                                                       __half* __restrict__ dst, int ld_dst, int c_off, int lo_dst, size_t npix, int gs, int fmt,
+                                                       const float* __restrict__ psi_pre) {      // non-NULL: psi per pixel is given (f_int = 0)
     extern __shared__ float s_wp[];
     for (int i = threadIdx.x; i < f_int; i += blockDim.x) s_wp[i] = w_psi[i];
     __syncthreads();
@@ -247,7 +366,7 @@ __global__ void __launch_bounds__(256) att_gate_kernel(const __half* __restrict_
         }
         for (int d = gs >> 1; d > 0; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d);
         const float z = fmaf(dot, psi_scale, psi_shift);
-        const float psi = 1.0f / (1.0f + expf(-z));
+        const float psi = psi_pre ? (live ? __ldg(psi_pre + pix) : 0.0f) : 1.0f / (1.0f + expf(-z));
         if (live) {
             const __half* xp = x + pix * ld_x;
             __half* op = dst + pix * ld_dst;
@@ -335,7 +454,10 @@ extern "C" int nbp_conv_first(const float* x, int n, int c_in, int h, int w, con
     const size_t smem = sizeof(float) * (size_t)(9 * c_in * 64 + 128 + 4 * 32 * CF_ROW);
     if (smem > 48 * 1024) return invalid("nbp_conv_first: c_in=%d needs more than 48 KB of shared memory", c_in);
     const int g = grid_for((size_t)n * h * w, 128);
-    if (c_in == 5) conv_first_kernel<64, 5><<<g, 128, smem, (cudaStream_t)stream>>>(x, n, c_in, h, w, weight, scale, shift, (__half*)dst, dst_ld, dst_lo, relu, fmt);
+    static int pair_env = -1;                             // NBP_STEM_PAIR=0: A/B switch back to the one-pixel-per-thread kernel
+    if (pair_env < 0) { const char* e = getenv("NBP_STEM_PAIR"); pair_env = e ? atoi(e) : 1; }
+    if (c_in == 5 && !(w & 1) && pair_env) conv_first5_kernel<<<g, 128, smem, (cudaStream_t)stream>>>(x, n, h, w, weight, scale, shift, (__half*)dst, dst_ld, dst_lo, relu, fmt);
+    else if (c_in == 5) conv_first_kernel<64, 5><<<g, 128, smem, (cudaStream_t)stream>>>(x, n, c_in, h, w, weight, scale, shift, (__half*)dst, dst_ld, dst_lo, relu, fmt);
     else conv_first_kernel<64, 0><<<g, 128, smem, (cudaStream_t)stream>>>(x, n, c_in, h, w, weight, scale, shift, (__half*)dst, dst_ld, dst_lo, relu, fmt);
     count_launch();
     return check_cuda(cudaGetLastError(), "nbp_conv_first launch");
@@ -389,9 +511,28 @@ extern "C" int nbp_att_gate(const void* a, int f_int, int ld_a, int lo_a, const 
     const size_t warps = ((size_t)npix + (32 / gs) - 1) / (32 / gs);
     att_gate_kernel<<<grid_for(warps * 32, 256, 2), 256, sizeof(float) * f_int, (cudaStream_t)stream>>>(
         (const __half*)a, f_int, ld_a, lo_a, (const __half*)x, f_l, ld_x, lo_x, w_psi, psi_scale, psi_shift,
-        (__half*)dst, dst_ld, dst_c_off, dst_lo, (size_t)npix, gs, fmt);
+        (__half*)dst, dst_ld, dst_c_off, dst_lo, (size_t)npix, gs, fmt, nullptr);
     count_launch();
     return check_cuda(cudaGetLastError(), "nbp_att_gate launch");
+}
+
+extern "C" int nbp_att_scale(const float* psi, const void* x, int f_l, int ld_x, int lo_x,
+                             void* dst, int dst_ld, int dst_c_off, int dst_lo, int64_t npix, int fmt, void* stream) {
+    if (!psi || !x || !dst) return invalid("nbp_att_scale: null pointer argument");
+    if (int rf = check_fmt("nbp_att_scale", fmt, fmt == 2 ? (lo_x | dst_lo | (dst_c_off % 64 ? 1 : 0)) : 64)) return rf;
+    if (f_l <= 0 || f_l % 8 || npix <= 0) return invalid("nbp_att_scale: bad sizes f_l=%d npix=%lld", f_l, (long long)npix);
+    int rc = check_plane("nbp_att_scale(x)", f_l, ld_x, lo_x);
+    if (rc) return rc;
+    if (dst_ld % 8 || dst_c_off % 8 || dst_lo % 8 || dst_c_off + dst_lo + f_l > dst_ld) return invalid("nbp_att_scale: bad destination layout");
+    if (((uintptr_t)x | (uintptr_t)dst) & 15) return invalid("nbp_att_scale: pointers must be 16-byte aligned");
+    int gs = 1;
+    while (gs * 2 <= 32 && gs * 2 <= f_l / 8) gs *= 2;
+    const size_t warps = ((size_t)npix + (32 / gs) - 1) / (32 / gs);
+    att_gate_kernel<<<grid_for(warps * 32, 256, 2), 256, 0, (cudaStream_t)stream>>>(
+        nullptr, 0, 0, 0, (const __half*)x, f_l, ld_x, lo_x, nullptr, 1.0f, 0.0f,
+        (__half*)dst, dst_ld, dst_c_off, dst_lo, (size_t)npix, gs, fmt, psi);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "nbp_att_scale launch");
 }
 
 extern "C" int nbp_conv1x1_head(const void* src, int c_in, int ld_src, int lo_src, const float* weight, const float* bias, int c_out,

@@ -9,6 +9,8 @@
 // them to cells with op-for-op pinned fp32 arithmetic (so cell indices are bit-exact with torch), and
 // warp-aggregates equal cells (__match_any_sync) into one fp32 RED.ADD per distinct cell per warp.
 // Counts are integers < 2^24, so fp32 accumulation is exact and order-independent.
+#include <cstdlib>
+
 #include "nbp_common.cuh"
 
 namespace nbp {
@@ -103,6 +105,91 @@ __global__ void __launch_bounds__(SC_THREADS) grid_scatter(ScatterParams p) {
     }
 }
 
+// Rollout clouds hit the same wall cells again and again (every frame that sees a wall adds ~10 points per cell and height slab), and
+// the kernel above is then limited by same-address fp32 REDs in L2 (ncu: 19 M RED sectors per 48 M points, 0.26 of the HBM peak), not
+// by the 12 bytes per point it streams.  This variant gives every CTA a contiguous chunk of SH_CHUNK_GROUPS * 4 points (~3 frames of a
+// rollout) and counts it in a shared-memory hash table (open addressing, integer counts) first; each distinct cell of the chunk then
+// costs ONE RED.  Counts are integers, so the grid is bit-identical to the direct kernel's; a crowded table (16 probes) falls back to
+// a direct RED for that point.
+static constexpr int SH_THREADS = 512;
+static constexpr int SH_SLOTS = 8192;                      // 32 KB keys + 32 KB counts
+static constexpr int SH_CHUNK_GROUPS = 4096;               // groups of 4 points per chunk
+
+__global__ void __launch_bounds__(SH_THREADS) grid_scatter_hash(ScatterParams p) {
+    extern __shared__ int sh_tab[];
+    volatile int* keys = sh_tab;
+    int* cnts = sh_tab + SH_SLOTS;
+    const int scene = blockIdx.y;
+    const int n = p.cloud_len[scene];
+    __shared__ float s_b[SC_MAX_BOUNDS];
+    __shared__ float s_c[2];
+    __shared__ int s_nb;
+    if (threadIdx.x < SC_MAX_BOUNDS)
+        s_b[threadIdx.x] = threadIdx.x < p.max_bounds ? p.bounds[(size_t)scene * p.max_bounds + threadIdx.x] : 0.0f;
+    if (threadIdx.x == 0) {
+        s_c[0] = p.pose[scene * 5 + 0]; s_c[1] = p.pose[scene * 5 + 2];
+        s_nb = min(p.n_bounds[scene], p.max_bounds);
+    }
+    __syncthreads();
+    float b[SC_MAX_BOUNDS];
+#pragma unroll
+    for (int q = 0; q < SC_MAX_BOUNDS; ++q) b[q] = s_b[q];
+    const int nb = s_nb;
+    const float cx = s_c[0], cz = s_c[1];
+    float* g = p.grid + (size_t)scene * (size_t)(p.n_pieces + 1) * p.S * p.S;
+    const float4* src = reinterpret_cast<const float4*>(p.cloud + (size_t)scene * (size_t)p.cap * 3);
+    const int n_groups = (n + 3) / 4;
+    const int n_chunks = (n_groups + SH_CHUNK_GROUPS - 1) / SH_CHUNK_GROUPS;
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        for (int i = threadIdx.x; i < SH_SLOTS; i += SH_THREADS) { keys[i] = -1; cnts[i] = 0; }
+        __syncthreads();
+        const int g1 = min(n_groups, (chunk + 1) * SH_CHUNK_GROUPS);
+        for (int gi = chunk * SH_CHUNK_GROUPS + threadIdx.x; gi < g1; gi += SH_THREADS) {
+            const float4 a = __ldcs(src + 3 * (size_t)gi), bq = __ldcs(src + 3 * (size_t)gi + 1), c = __ldcs(src + 3 * (size_t)gi + 2);
+            const float v[12] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int k = 0; k < SC_PTS_PER_THREAD; ++k) {
+                if (4 * gi + k >= n) break;
+                const int cell = point_cell(v[3 * k], v[3 * k + 1], v[3 * k + 2], cx, cz, b, nb, p.n_pieces, p.S, p.lo, p.scale);
+                if (cell < 0) continue;
+                unsigned slot = ((unsigned)cell * 2654435761u) >> 19;            // 13 bits
+                bool done = false;
+#pragma unroll 1
+                for (int probe = 0; probe < 16 && !done; ++probe) {
+                    int cur = keys[slot];
+                    if (cur == -1) cur = atomicCAS(const_cast<int*>(keys) + slot, -1, cell);
+                    if (cur == cell || cur == -1) { atomicAdd(cnts + slot, 1); done = true; }
+                    slot = (slot + 1) & (SH_SLOTS - 1);
+                }
+                if (!done) atomicAdd(g + cell, 1.0f);
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < SH_SLOTS; i += SH_THREADS) {
+            const int key = keys[i];
+            if (key >= 0) atomicAdd(g + key, (float)cnts[i]);
+        }
+        __syncthreads();
+    }
+
+    // ---- the trajectory image (channel n_pieces): a few hundred points, first CTA of the scene
+    if (blockIdx.x == 0 && p.traj) {
+        const int nt = p.traj_len[scene];
+        const float* t = p.traj + (size_t)scene * (size_t)p.tcap * 3;
+        float* gt = g + (size_t)p.n_pieces * p.S * p.S;
+        const int padded = (nt + 31) & ~31;
+        for (int i = threadIdx.x; i < padded; i += SH_THREADS) {
+            int cell = -1;
+            if (i < nt) {
+                const float r = cell_coord(-fsub(t[3 * i + 2], cz), p.lo, p.scale);
+                const float c = cell_coord(-fsub(t[3 * i + 0], cx), p.lo, p.scale);
+                if (r >= 0.0f && r < (float)p.S && c >= 0.0f && c < (float)p.S) cell = (int)r * p.S + (int)c;
+            }
+            warp_aggregated_add(gt, cell);
+        }
+    }
+}
+
 // plain map_points_to_n_imgs: points_2d [n, m, 2]
 __global__ void __launch_bounds__(SC_THREADS) map_points_kernel(const float* pts, const int32_t* lens, int64_t m, int S0, int S1,
                                                                 float lo, float sx, float sy, float* out) {
@@ -162,6 +249,24 @@ extern "C" int nbp_grid_scatter(const float* cloud, const int32_t* cloud_len, in
     const float scale = (float)((double)S / ((double)range_hi - (double)range_lo));
     ScatterParams p{cloud, cloud_len, cloud_capacity, traj, traj_len, traj_capacity, pose, slab_bounds, n_bounds, max_bounds,
                     n_pieces, S, range_lo, scale, grid};
+    // clouds of a few frames or more go through the shared-memory hash (NBP_SCATTER_HASH=0: always the direct kernel, A/B switch)
+    static int hash_env = -1;
+    if (hash_env < 0) { const char* e = getenv("NBP_SCATTER_HASH"); hash_env = e ? atoi(e) : 1; }
+    if (hash_env && groups >= 2 * SH_CHUNK_GROUPS) {
+        static bool attr_d[NBP_MAX_DEVICES] = {};
+        bool& attr = attr_d[device_slot()];
+        const int smem = SH_SLOTS * 2 * (int)sizeof(int);
+        if (!attr) {
+            rc = check_cuda(cudaFuncSetAttribute(grid_scatter_hash, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "cudaFuncSetAttribute(grid_scatter_hash)");
+            if (rc) return rc;
+            attr = true;
+        }
+        int hx = (int)((groups + SH_CHUNK_GROUPS - 1) / SH_CHUNK_GROUPS);
+        if (hx > 148 * 4) hx = 148 * 4;
+        grid_scatter_hash<<<dim3(hx, n_scenes), SH_THREADS, smem, st>>>(p);
+        count_launch();
+        return check_cuda(cudaGetLastError(), "nbp_grid_scatter launch");
+    }
     grid_scatter<<<dim3(gx, n_scenes), SC_THREADS, 0, st>>>(p);
     count_launch();
     return check_cuda(cudaGetLastError(), "nbp_grid_scatter launch");

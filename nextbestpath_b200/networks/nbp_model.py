@@ -13,6 +13,7 @@ fallback: CPU tensors raise.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -168,6 +169,8 @@ def _affine(sd, conv, bn, eps=1e-5):
 
 
 LO_SCALE = 2048.0
+# A/B switch (NBP_FUSE_DOT=0): psi of the attention gates and the Final2 head as separate kernels instead of the conv kernel's dot epilogue
+FUSE_DOT = os.environ.get("NBP_FUSE_DOT", "1") != "0"
 
 
 def _pack_gemm_weight(w2d, precise):
@@ -281,7 +284,8 @@ def pack_state_dict(sd, precise=True, e4m3_layers=None):
                        extra={"w_psi": sd[f"Att{t}.psi.0.weight"].reshape(-1).contiguous(),
                               "psi_scale": float(sp.item()), "psi_shift": float(bp.item())})
     pk["Final1"] = {"w": sd["Final1.weight"][:, :, 0, 0].contiguous(), "b": sd["Final1.bias"].contiguous()}
-    pk["Final2"] = {"w": sd["Final2.0.weight"][:, :, 0, 0].contiguous(), "b": sd["Final2.0.bias"].contiguous()}
+    pk["Final2"] = {"w": sd["Final2.0.weight"][:, :, 0, 0].contiguous(), "b": sd["Final2.0.bias"].contiguous(),
+                    "b_host": float(sd["Final2.0.bias"].reshape(-1)[0].item())}
     return pk
 
 
@@ -308,7 +312,9 @@ class _Act:
         return _Act(self.t, c, self.ld, self.lo, self.h, self.w, self.off + off, self.fmt)
 
 
-def _conv(pk, layer, B, src0, taps, dst, relu=True, src1=None, up2x=False, k_chunk=0, pool=None):
+def _conv(pk, layer, B, src0, taps, dst, relu=True, src1=None, up2x=False, k_chunk=0, pool=None, dot=None):
+    """``dot`` = (w [c_out] fp32, scale, shift, sigmoid, out fp32 [B,h,w]): the dot epilogue of nbp_conv_desc -- the layer's output is
+    contracted with ``w`` per pixel instead of being stored (``dst`` is None then)."""
     mode = layer.get("mode", 1 if pk["precise"] else 0)
     if mode and (src0.fmt != mode or (src1 is not None and src1.fmt != mode)):
         raise RuntimeError(f"conv in mode {mode} got sources in format {src0.fmt}" + (f"/{src1.fmt}" if src1 is not None else ""))
@@ -317,9 +323,12 @@ def _conv(pk, layer, B, src0, taps, dst, relu=True, src1=None, up2x=False, k_chu
                       src1.ld if src1 is not None else 0, src1.lo if src1 is not None else 0,
                       B, src0.h, src0.w, taps, 1 if up2x else 0, layer["w"].data_ptr(), layer["c_out"],
                       layer["scale"].data_ptr(), layer["shift"].data_ptr(), 1 if relu else 0,
-                      dst.t.data_ptr(), dst.ld, dst.off, dst.lo, 0, k_chunk,
-                      dst.fmt if mode else 0, (pool.fmt if pool is not None else 0) if mode else 0, layer.get("lo_scale", 1.0 / LO_SCALE),
-                      pk["sat_count"].data_ptr() if "sat_count" in pk else None, pool.ptr if pool is not None else None, pool.ld if pool is not None else 0, pool.lo if pool is not None else 0)
+                      dst.t.data_ptr() if dst is not None else None, dst.ld if dst is not None else 0, dst.off if dst is not None else 0,
+                      dst.lo if dst is not None else 0, 0, k_chunk,
+                      (dst.fmt if mode else 0) if dst is not None else 0, (pool.fmt if pool is not None else 0) if mode else 0, layer.get("lo_scale", 1.0 / LO_SCALE),
+                      pk["sat_count"].data_ptr() if "sat_count" in pk else None, pool.ptr if pool is not None else None, pool.ld if pool is not None else 0, pool.lo if pool is not None else 0,
+                      dot[0].data_ptr() if dot is not None else None, dot[4].data_ptr() if dot is not None else None,
+                      dot[1] if dot is not None else 0.0, dot[2] if dot is not None else 0.0, (1 if dot[3] else 0) if dot is not None else 0)
     _lib.check(_lib.lib().nbp_conv_fwd(ctypes.byref(d), _stream()), "nbp_conv_fwd")
 
 
@@ -379,11 +388,15 @@ def _forward_eval(pk, x, out1, out2, vmax):
             raise RuntimeError(f"layers {names} read the same tensor and must run the same numeric mode")
         return m.pop()
 
-    def double_conv(name, src, out_fmt, pool_fmt=None):
-        """conv_block (nbp_model.py:8-21); ``pool_fmt``: the second conv also writes MaxPool2d(2,2) of its output (:113-121)."""
+    def double_conv(name, src, out_fmt, pool_fmt=None, dot=None):
+        """conv_block (nbp_model.py:8-21); ``pool_fmt``: the second conv also writes MaxPool2d(2,2) of its output (:113-121);
+        ``dot``: the second conv feeds a fused 1-channel 1x1 head instead of storing its output (returns None, None)."""
         c_out = pk[name + ".a"]["c_out"]
         t = new(src.h, src.w, c_out, mode(name + ".b"))
         _conv(pk, pk[name + ".a"], B, src, 9, t)
+        if dot is not None:
+            _conv(pk, pk[name + ".b"], B, t, 9, None, dot=dot)
+            return None, None
         y = new(src.h, src.w, c_out, out_fmt)
         p = new(src.h // 2, src.w // 2, c_out, pool_fmt) if pool_fmt is not None else None
         _conv(pk, pk[name + ".b"], B, t, 9, y, pool=p)
@@ -408,7 +421,7 @@ def _forward_eval(pk, x, out1, out2, vmax):
         skips[lvl], p = double_conv(f"Conv{lvl}", p, stage_fmt[lvl + 1], pool_fmt=mode(f"Conv{lvl + 1}.a"))
     skips[5], _ = double_conv("Conv5", p, same("Up5_1", "Up5_2"))
 
-    def decoder_stage(d, lvl, dec, out_fmt):
+    def decoder_stage(d, lvl, dec, out_fmt, dot=None):
         """Up{lvl}_{dec} -> Att{lvl}_{dec} -> cat -> Up_conv{lvl}_{dec} (nbp_model.py:124-129)."""
         t = f"{lvl}_{dec}"
         skip = skips[lvl - 1]
@@ -418,14 +431,22 @@ def _forward_eval(pk, x, out1, out2, vmax):
         g = cat.channels(f_l, f_l)
         _conv(pk, pk[f"Up{t}"], B, d, 4, g, up2x=True)   # upsample fused: d is read at its own (half) resolution
         att = pk[f"Att{t}"]
-        arelu = new(skip.h, skip.w, att["c_out"], 1)     # read by the gate kernel only (f_int can be 32 < one e4m3 group): 22-bit format
-        _conv(pk, att, B, g, 1, arelu, relu=True, src1=skip)
         gated = cat.channels(0, f_l)
-        _lib.check(L.nbp_att_gate(arelu.ptr, arelu.c, arelu.ld, arelu.lo, skip.ptr, f_l, skip.ld, skip.lo,
-                                  att["w_psi"].data_ptr(), att["psi_scale"], att["psi_shift"],
-                                  gated.t.data_ptr(), gated.ld, gated.off, gated.lo, B * skip.h * skip.w, fmt, st), "nbp_att_gate")
-        del arelu
-        return double_conv(f"Up_conv{t}", cat, out_fmt)[0]
+        if FUSE_DOT and att["c_out"] <= 128:
+            # psi = sigmoid(BN(w_psi . a)) leaves the attention GEMM's epilogue directly (dot epilogue): `a` never goes to memory
+            psi = torch.empty((B, skip.h, skip.w), dtype=torch.float32, device=dev)
+            _conv(pk, att, B, g, 1, None, relu=True, src1=skip, dot=(att["w_psi"], att["psi_scale"], att["psi_shift"], True, psi))
+            _lib.check(L.nbp_att_scale(psi.data_ptr(), skip.ptr, f_l, skip.ld, skip.lo,
+                                       gated.t.data_ptr(), gated.ld, gated.off, gated.lo, B * skip.h * skip.w, fmt, st), "nbp_att_scale")
+            del psi
+        else:
+            arelu = new(skip.h, skip.w, att["c_out"], 1)     # read by the gate kernel only (f_int can be 32 < one e4m3 group): 22-bit format
+            _conv(pk, att, B, g, 1, arelu, relu=True, src1=skip)
+            _lib.check(L.nbp_att_gate(arelu.ptr, arelu.c, arelu.ld, arelu.lo, skip.ptr, f_l, skip.ld, skip.lo,
+                                      att["w_psi"].data_ptr(), att["psi_scale"], att["psi_shift"],
+                                      gated.t.data_ptr(), gated.ld, gated.off, gated.lo, B * skip.h * skip.w, fmt, st), "nbp_att_gate")
+            del arelu
+        return double_conv(f"Up_conv{t}", cat, out_fmt, dot=dot)[0]
 
     def head(name, d, sigmoid, out, out_max=None):
         _lib.check(L.nbp_conv1x1_head(d.ptr, d.c, d.ld, d.lo, pk[name]["w"].data_ptr(), pk[name]["b"].data_ptr(),
@@ -439,6 +460,11 @@ def _forward_eval(pk, x, out1, out2, vmax):
     head("Final1", d, False, out1, vmax)
     # ---- decoder 2 -> obstacle map at S
     d = decoder_stage(skips[5], 5, 2, mode("Up4_2"))
-    for lvl in (4, 3, 2):
-        d = decoder_stage(d, lvl, 2, mode(f"Up{lvl - 1}_2") if lvl > 2 else 1)
-    head("Final2", d, True, out2)
+    for lvl in (4, 3):
+        d = decoder_stage(d, lvl, 2, mode(f"Up{lvl - 1}_2"))
+    f2 = pk["Final2"]
+    if FUSE_DOT and f2["w"].shape[0] == 1 and f2["w"].shape[1] in (32, 64, 128):
+        # Final2 (1x1 conv to one channel + sigmoid, nbp_model.py:106-108) inside the epilogue of Up_conv2_2's second conv
+        decoder_stage(d, 2, 2, 1, dot=(f2["w"].reshape(-1), 1.0, f2["b_host"], True, out2))
+    else:
+        head("Final2", decoder_stage(d, 2, 2, 1), True, out2)

@@ -223,6 +223,22 @@ def test_grid_scatter_bit_exact_vs_oracle(S):
     assert out[:, :4].sum() > 10000 and out[:, 4].sum() > 5
 
 
+@pytest.mark.parametrize("S,n_pts", [(256, 150000), (512, 150000), (128, 40000)])
+def test_grid_scatter_large_clouds_take_the_hash_path_bit_exact(S, n_pts):
+    """Clouds of >= 32768 points per scene are counted per 16384-point chunk in a shared-memory hash table before they reach the grid
+    (grid_scatter_hash).  Ragged lengths (scene 0 full, the others anywhere from empty), clustered and uniform points: at S = 512 a
+    chunk holds more distinct cells than the table has slots, so the crowded-table fallback runs too.  Same bits as the numpy oracle."""
+    cloud, lens, pose, bounds, nb, traj, tl, ybs = _scatter_inputs(4, n_pts, seed=S + 1)
+    t = lambda a: torch.from_numpy(a).to(DEV)
+    out = ops.grid_scatter(t(cloud), t(lens), t(pose), t(bounds), t(nb), S, traj=t(traj), traj_len=t(tl))
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    for s in range(cloud.shape[0]):
+        want = O.build_model_input(cloud[s, : lens[s]], pose[s], ybs[s][:-1], traj[s, : tl[s]], S)
+        assert np.array_equal(out[s], want), f"scene {s}: {(out[s] != want).sum()} cells differ"
+    assert out[:, :4].sum() > n_pts // 4
+
+
 def test_grid_scatter_matches_reference_fixture(golden_dir):
     """The fixture was produced by the reference's own bucketize + transform_points_to_n_pieces +
     map_points_to_n_imgs (tests/golden/make_golden.py)."""

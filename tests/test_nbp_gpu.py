@@ -227,6 +227,21 @@ def test_pointwise_kernels_match_torch(precise):
                                 planes * 64, 64 if precise else 0, 1, _st()), "stem")
     ref = F.relu(F.conv2d(xin.double(), w0.double(), padding=1) * sc.double()[None, :, None, None] + sh.double()[None, :, None, None]).permute(0, 2, 3, 1).float()
     assert (_from_act(dst, 64, 64 if precise else 0) - ref).abs().max() <= (3e-6 if precise else 1e-3) * ref.abs().max()
+    # the two stem kernels (pixel-pair fp32x2 kernel for even widths, generic kernel otherwise / NBP_STEM_PAIR=0) sum every output in the
+    # same order: plain fp32 destinations (train mode) of an even-width image and of its odd-width crop agree bit for bit where their
+    # receptive fields coincide, and both match the float64 convolution
+    for wcrop in (32, 31):
+        xc = xin[:, :, :, :wcrop].contiguous().to(DEV)
+        raw = torch.empty((2, 32, wcrop, 64), dtype=torch.float32, device=DEV)
+        _lib.check(L.nbp_conv_first(xc.data_ptr(), 2, 5, 32, wcrop, wp.data_ptr(), scd.data_ptr(), shd.data_ptr(), 64, 0, raw.data_ptr(),
+                                    64, -1, 1, _st()), "stem fp32")
+        refc = (F.conv2d(xin[:, :, :, :wcrop].double(), w0.double(), padding=1) * sc.double()[None, :, None, None]
+                + sh.double()[None, :, None, None]).permute(0, 2, 3, 1)
+        assert (raw.cpu().double() - refc).abs().max() <= 3e-6 * refc.abs().max()
+        if wcrop == 32:
+            raw_even = raw.cpu()
+        else:
+            assert torch.equal(raw.cpu()[:, :, :30], raw_even[:, :, :30])
 
 
 def _errs(a, b):
@@ -392,6 +407,56 @@ def test_conv_fwd_e4m3_correction_mode(n, h, w, c0, c1, cout, taps, up):
     assert rel(v2, want) <= 3e-5                                   # fmt-2 output keeps hi + e4m3 lo: 2^-15
     assert torch.equal(outs[2][..., :cout], outs[1][..., :cout])   # same hi plane in both formats
     assert rel(q2, want) <= 4e-2                                   # the e4m3 copy of the value: 3 mantissa bits
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("n,h,w,c0,c1,cout,taps,up", [(2, 16, 16, 128, 128, 64, 1, 0), (1, 32, 32, 64, 64, 32, 1, 0), (7, 16, 16, 64, 64, 128, 1, 0),
+                                                       (3, 8, 16, 64, 0, 64, 9, 0), (3, 8, 16, 128, 0, 128, 9, 0), (2, 16, 16, 128, 0, 64, 4, 1),
+                                                       (5, 4, 4, 192, 0, 64, 9, 0)])
+def test_conv_dot_epilogue_equals_conv_then_1x1(n, h, w, c0, c1, cout, taps, up, mode):
+    """nbp_conv_desc.dot_out: the layer's activations are contracted with a vector inside the epilogue (Attention_block.psi, Final2)
+    instead of being stored.  Checked against the SAME launch writing its output (22-bit fp16x2 planes) followed by the 1x1
+    convolution in float64: every kernel variant the network uses it with (plain / pair / halo / fused up-sampling, N = 32, 64, 128,
+    ghost tiles), with and without the sigmoid."""
+    from nextbestpath_b200.networks import nbp_model as M
+    g = torch.Generator().manual_seed(n * 1000 + h + c0 + cout + taps + mode)
+    x = torch.randn(n, c0 + c1, h, w, generator=g) * 1.5
+    k = 3 if taps != 1 else 1
+    wt = torch.randn(cout, c0 + c1, k, k, generator=g) / ((c0 + c1) * k * k) ** 0.5
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    if up:
+        rows = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+        blocks = [torch.stack([sum(wt[:, :, ky, kx] for ky in rows[py][ty] for kx in rows[px][tx]) for ty in (0, 1) for tx in (0, 1)], dim=1)
+                  .reshape(cout, -1) for py in (0, 1) for px in (0, 1)]
+    else:
+        blocks = [wt.permute(0, 2, 3, 1).reshape(cout, -1)]
+    if mode == 2:
+        sw = M._e4m3_weight_scale(torch.cat([b.reshape(-1) for b in blocks]))
+        wp = torch.cat([M._pack_gemm_weight_e4m3(b, sw) for b in blocks], dim=0).contiguous().to(DEV)
+        layer = {"w": wp, "c_out": cout, "scale": scale.to(DEV), "shift": shift.to(DEV), "mode": 2, "lo_scale": 1.0 / (2048.0 * sw)}
+        a0 = M._Act(*_to_act_fmt2(x[:, :c0]), h, w, 0, 2)
+        a1 = M._Act(*_to_act_fmt2(x[:, c0:]), h, w, 0, 2) if c1 else None
+    else:
+        wp = torch.cat([M._pack_gemm_weight(b, True) for b in blocks], dim=0).contiguous().to(DEV)
+        layer = {"w": wp, "c_out": cout, "scale": scale.to(DEV), "shift": shift.to(DEV), "mode": 1}
+        a0 = M._Act(*_to_act(x[:, :c0], True), h, w, 0, 1)
+        a1 = M._Act(*_to_act(x[:, c0:], True), h, w, 0, 1) if c1 else None
+    oh, ow = (2 * h, 2 * w) if up else (h, w)
+    y = M._Act(torch.zeros((n, oh, ow, 2 * cout), dtype=torch.float16, device=DEV), cout, 2 * cout, cout, oh, ow, 0, 1)
+    M._conv({"precise": True}, layer, n, a0, taps, y, relu=True, src1=a1, up2x=bool(up))
+    torch.cuda.synchronize()
+    act = _from_act(y.t, cout, cout).double()                                   # (n, oh, ow, cout)
+    wv = torch.randn(cout, generator=g) / cout ** 0.5
+    wv_d = wv.to(DEV)
+    for sig in (True, False):
+        out = torch.full((n, oh, ow), 7.0, dtype=torch.float32, device=DEV)
+        M._conv({"precise": True}, layer, n, a0, taps, None, relu=True, src1=a1, up2x=bool(up), dot=(wv_d, 1.7, -0.3, sig, out))
+        torch.cuda.synchronize()
+        z = (act * wv.double()).sum(-1) * 1.7 - 0.3
+        ref = torch.sigmoid(z) if sig else z
+        bound = 3e-6 * ((act.abs() * wv.double().abs()).sum(-1) * 1.7 + 1.0)    # fp32 dot of un-rounded activations vs the 22-bit stored ones
+        err = (out.cpu().double() - ref).abs()
+        assert (err <= bound).all(), f"max err {err.max().item():.3e}"
 
 
 def test_nbp_graph_replay_equals_eager_and_tracks_inputs_and_weights():
