@@ -87,6 +87,10 @@ int nbp_raster_depth_batched(const float* verts, const int32_t* faces,
  * frame_valid / frame_kept [n_frames] int32 receive n and k (may be NULL).
  */
 size_t nbp_backproject_workspace_bytes(int n_frames);
+/* Optional extra scratch: a workspace of nbp_backproject_workspace_bytes(n) + nbp_backproject_key_cache_bytes(n, H, W) bytes lets the
+ * sub-sampling path (gathering_factor < 1) evaluate every pixel's selection key once (4 bytes per pixel kept in the scratch) instead of
+ * once per selection pass and once more when writing; the result is identical. */
+size_t nbp_backproject_key_cache_bytes(int n_frames, int H, int W);
 int nbp_backproject_append(const float* zbuf, const uint8_t* mask, const float* R, const float* T,
                            const int32_t* frame_scene, const int32_t* frame_uid, int n_frames,
                            int H, int W, float tan_half_fov, float fov_range,

@@ -26,6 +26,7 @@ SIGNATURES = {
     "nbp_raster_workspace_bytes": (_z, [_i, _l]),
     "nbp_raster_depth_batched": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _i, _l, _i, _i, _i, _f, _f, _p, _p, _p, _z, _p]),
     "nbp_backproject_workspace_bytes": (_z, [_i]),
+    "nbp_backproject_key_cache_bytes": (_z, [_i, _i, _i]),
     "nbp_backproject_append": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, C.c_double, C.c_uint64,
                                     _p, _p, _l, _i, _p, _p, _p, _p, _z, _p]),
     "nbp_grid_scatter": (_i, [_p, _p, _l, _p, _p, _l, _p, _p, _p, _i, _i, _i, _i, _f, _f, _l, _p, _p]),

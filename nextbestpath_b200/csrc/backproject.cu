@@ -59,7 +59,10 @@ struct BpParams {
     float* cloud; int32_t* cloud_len; int64_t cap; int n_scenes;
     int32_t* frame_valid; int32_t* frame_kept; int32_t* overflow;
     FrameSel* sel;
+    uint32_t* keys;        // optional [n_frames][HW] scratch: the key of every pixel (BP_NO_KEY = invalid pixel), written by the first select
+                           // pass and read by the later passes and by bp_write instead of re-evaluating validity + the 6-round Feistel key
 };
+static constexpr uint32_t BP_NO_KEY = 0xffffffffu;        // keys have at most 26 bits
 
 __device__ __forceinline__ bool depth_valid(const BpParams& p, float d, bool masked_in) {
     bool v = masked_in;                            // an explicit mask replaces the default zbuf > -1 (macarons_utils.py:2771,2825)
@@ -116,19 +119,42 @@ __global__ void __launch_bounds__(BP_THREADS) bp_select(BpParams p) {
         __syncthreads();
         const uint32_t prefix = s_prefix;                    // already-fixed high bits (aligned at `bits_left`)
         int cnt = 0;
-        auto visit = [&](int i) {
-            if (!subsample) { ++cnt; return; }
-            const uint32_t key = perm((uint32_t)i);
+        auto tally = [&](uint32_t key) {
             if ((key >> bits_left) != prefix) return;
             atomicAdd(&s_hist[(key >> shift) & ((1u << db) - 1u)], 1);
         };
-        for (int q = threadIdx.x; q < nq; q += BP_THREADS) {
-            float d4[4];
-            const unsigned v = quad_valid(p, z, m, q, d4);
+        uint32_t* kf = (p.keys && subsample) ? p.keys + (size_t)f * p.HW : nullptr;
+        if (kf && !first) {
+            // later passes: the keys are in the scratch (L2), no depth read and no key evaluation
+            for (int q = threadIdx.x; q < nq; q += BP_THREADS) {
+                const uint4 k4 = *(reinterpret_cast<const uint4*>(kf) + q);
+                if (k4.x != BP_NO_KEY) tally(k4.x);
+                if (k4.y != BP_NO_KEY) tally(k4.y);
+                if (k4.z != BP_NO_KEY) tally(k4.z);
+                if (k4.w != BP_NO_KEY) tally(k4.w);
+            }
+            if (!vec) for (int i = threadIdx.x; i < p.HW; i += BP_THREADS) { const uint32_t k1 = kf[i]; if (k1 != BP_NO_KEY) tally(k1); }
+        } else {
+            for (int q = threadIdx.x; q < nq; q += BP_THREADS) {
+                float d4[4];
+                const unsigned v = quad_valid(p, z, m, q, d4);
+                if (!subsample) { cnt += __popc(v); continue; }
+                uint32_t k4[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if ((v >> j) & 1u) visit(4 * q + j);
+                for (int j = 0; j < 4; ++j) {
+                    k4[j] = BP_NO_KEY;
+                    if ((v >> j) & 1u) { k4[j] = perm((uint32_t)(4 * q + j)); tally(k4[j]); }
+                }
+                if (kf) *(reinterpret_cast<uint4*>(kf) + q) = make_uint4(k4[0], k4[1], k4[2], k4[3]);
+            }
+            if (!vec) for (int i = threadIdx.x; i < p.HW; i += BP_THREADS) {
+                const bool v = pixel_valid(p, z, m, i);
+                if (!subsample) { cnt += v ? 1 : 0; continue; }
+                const uint32_t k1 = v ? perm((uint32_t)i) : BP_NO_KEY;
+                if (v) tally(k1);
+                if (kf) kf[i] = k1;
+            }
         }
-        if (!vec) for (int i = threadIdx.x; i < p.HW; i += BP_THREADS) if (pixel_valid(p, z, m, i)) visit(i);
         if (first && !subsample) {                           // keep everything: only the count is needed
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
@@ -224,6 +250,8 @@ __global__ void __launch_bounds__(BP_THREADS) bp_write(BpParams p) {
     float* out = p.cloud + (size_t)scene * (size_t)p.cap * 3;
     const int warp = threadIdx.x >> 5, lane = lane_id(), nwarp = BP_THREADS / 32;
     int dropped = 0;
+    const uint32_t* kf = (p.keys && p.gf < 1.0) ? p.keys + (size_t)f * p.HW : nullptr;    // keys left by bp_select (BP_NO_KEY = invalid pixel)
+    const uint32_t tau_all = all ? BP_NO_KEY - 1u : sel.tau;                              // keep = key <= tau_all
 
     // every warp owns one contiguous range of pixels (row-major order is preserved).  Fast path: a lane reads 4 consecutive pixels per
     // iteration (one 16-byte load), decides keep / drop ONCE (validity + key <= tau), remembers the 4-bit decisions in registers, and after
@@ -241,7 +269,10 @@ __global__ void __launch_bounds__(BP_THREADS) bp_write(BpParams p) {
             if (it >= n_it) break;
             const int q = q0 + it * 32 + lane;
             unsigned mk = 0;
-            if (q < q1) {
+            if (q < q1 && kf) {
+                const uint4 k4 = *(reinterpret_cast<const uint4*>(kf) + q);
+                mk = (k4.x <= tau_all ? 1u : 0u) | (k4.y <= tau_all ? 2u : 0u) | (k4.z <= tau_all ? 4u : 0u) | (k4.w <= tau_all ? 8u : 0u);
+            } else if (q < q1) {
                 float d4[4];
                 mk = quad_valid(p, z, m, q, d4);
                 if (!all) {
@@ -291,7 +322,7 @@ __global__ void __launch_bounds__(BP_THREADS) bp_write(BpParams p) {
         int cnt = 0;
         for (int b = i0; b < i1; b += 32) {
             const int i = b + lane;
-            const bool kp = i < i1 && pixel_valid(p, z, m, i) && (all || perm((uint32_t)i) <= sel.tau);
+            const bool kp = i < i1 && (kf ? kf[i] <= tau_all : (pixel_valid(p, z, m, i) && (all || perm((uint32_t)i) <= sel.tau)));
             cnt += __popc(__ballot_sync(0xffffffffu, kp));
         }
         if (lane == 0) s_wcnt[warp] = cnt;
@@ -300,7 +331,7 @@ __global__ void __launch_bounds__(BP_THREADS) bp_write(BpParams p) {
         for (int w = 0; w < warp; ++w) running += s_wcnt[w];
         for (int b = i0; b < i1; b += 32) {
             const int i = b + lane;
-            const bool kp = i < i1 && pixel_valid(p, z, m, i) && (all || perm((uint32_t)i) <= sel.tau);
+            const bool kp = i < i1 && (kf ? kf[i] <= tau_all : (pixel_valid(p, z, m, i) && (all || perm((uint32_t)i) <= sel.tau)));
             const unsigned ball = __ballot_sync(0xffffffffu, kp);
             const int slot = running + __popc(ball & ((1u << lane) - 1u));
             running += __popc(ball);
@@ -320,6 +351,13 @@ using namespace nbp;
 extern "C" size_t nbp_backproject_workspace_bytes(int n_frames) {
     if (n_frames < 0) return 0;
     return sizeof(FrameSel) * (size_t)(n_frames + 1);
+}
+
+static size_t bp_sel_bytes(int n_frames) { return (sizeof(FrameSel) * (size_t)(n_frames + 1) + 255) / 256 * 256; }
+
+extern "C" size_t nbp_backproject_key_cache_bytes(int n_frames, int H, int W) {
+    if (n_frames < 0 || H <= 0 || W <= 0) return 0;
+    return bp_sel_bytes(n_frames) - nbp_backproject_workspace_bytes(n_frames) + sizeof(uint32_t) * (size_t)n_frames * (size_t)H * (size_t)W;
 }
 
 extern "C" int nbp_backproject_append(const float* zbuf, const uint8_t* mask, const float* R, const float* T,
@@ -351,7 +389,10 @@ extern "C" int nbp_backproject_append(const float* zbuf, const uint8_t* mask, co
     if (mn < 2) return invalid("nbp_backproject_append: H and W must be >= 2");
     BpParams p{zbuf, mask, R, T, frame_scene, frame_uid, n_frames, H, W, H * W, wm, hm, mm1, tan_half_fov, fov_range,
                gathering_factor, seed, key_bits, cloud, cloud_len, cloud_capacity, n_scenes,
-               frame_valid, frame_kept, overflow, (FrameSel*)workspace};
+               frame_valid, frame_kept, overflow, (FrameSel*)workspace, nullptr};
+    // a workspace that also holds nbp_backproject_key_cache_bytes() lets the kernels evaluate every pixel's key once instead of three times
+    if (gathering_factor < 1.0 && workspace_bytes >= need + nbp_backproject_key_cache_bytes(n_frames, H, W))
+        p.keys = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + bp_sel_bytes(n_frames));
     cudaStream_t st = (cudaStream_t)stream;
     bp_select<<<n_frames, BP_THREADS, 0, st>>>(p);
     count_launch();

@@ -843,8 +843,14 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     // K slices (64 elements each) per in-TMEM accumulation chain; 0 = unbounded.  The fp16+e4m3 mode keeps whole reductions in TMEM by
     // default: the truncating accumulator costs 1.2e-9 * K relative (1.1e-5 at K = 9216), an order below that mode's operand error
     const int want = d->k_chunk > 0 ? d->k_chunk : (fp8 ? k8_env : kchunk_env);
-    const bool halo = halo_env && precise && block_n <= 64 && (d->taps == 9 || d->up2x) && kp.tn == 1 && kp.tw >= 8 &&
-                      (kp.th + 2) * kp.tw <= HALO_ROWS && !(want > 0 && want < 3);
+    // 128-column tiles too, as CTA pairs: a pair stages only half of the weight rows per SM, so a halo stage (A block of one column
+    // offset + the weight tiles of its 3 taps) is 88 KB and two fit; per 64-channel slice and 3 taps an SM then takes in 88 KB instead
+    // of 3 x 48 KB.  Measured on the 32-scene forward: -7.8 % conv time, tensor pipe 82-92 % busy on those layers (was 70-83 %);
+    // NBP_CONV_HALO128=0 is the A/B switch back to plain split stages
+    static int halo128_env = -1;
+    if (halo128_env < 0) { const char* e = getenv("NBP_CONV_HALO128"); halo128_env = e ? atoi(e) : 1; }
+    const bool halo = halo_env && precise && (block_n <= 64 || (block_n == 128 && halo128_env && kp.m_tiles >= 2)) && (d->taps == 9 || d->up2x) &&
+                      kp.tn == 1 && kp.tw >= 8 && (kp.th + 2) * kp.tw <= HALO_ROWS && !(want > 0 && want < 3);
     static int split_env = -1, cluster_env = -1;
     if (cluster_env < 0) { const char* e = getenv("NBP_CONV_CLUSTER"); cluster_env = e ? atoi(e) : 2; }
     kp.cluster = (cluster_env >= 2 && kp.m_tiles >= 2) ? 2 : 1;
@@ -854,7 +860,7 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     if (pair_env < 0) { const char* e = getenv("NBP_CONV_PAIR"); pair_env = e ? atoi(e) : 1; }
     // cta_group::2 tiles (ConvCfg, PAIR): the 128-column plain launches of the fp16+e4m3 (split) and fp16x2 modes
     const bool pair = pair_env && kp.m_tiles >= 2 &&
-                      ((block_n == 128 && !halo && (split || d->precise == 1)) || (block_n == 64 && halo && precise));
+                      ((block_n == 128 && !halo && (split || d->precise == 1)) || (block_n >= 64 && halo && precise));
     if (pair) kp.cluster = 2;
     const int planes_ = split ? 1 : precise ? 2 : 1;                  // planes carried by one pipeline stage
     kp.gtaps = halo ? (d->up2x ? 2 : 3) : 1;
@@ -911,6 +917,10 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
         if (rc) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (pair && halo && block_n == 128) {
+        if (fp8) return d->up2x ? launch_conv<128, 2, 2, true>(a0, a1, b, kp, sms, st) : launch_conv<128, 2, 3, true>(a0, a1, b, kp, sms, st);
+        return d->up2x ? launch_conv<128, 1, 2, true>(a0, a1, b, kp, sms, st) : launch_conv<128, 1, 3, true>(a0, a1, b, kp, sms, st);
+    }
     if (pair && halo) {
         if (fp8) return d->up2x ? launch_conv<64, 2, 2, true>(a0, a1, b, kp, sms, st) : launch_conv<64, 2, 3, true>(a0, a1, b, kp, sms, st);
         return d->up2x ? launch_conv<64, 1, 2, true>(a0, a1, b, kp, sms, st) : launch_conv<64, 1, 3, true>(a0, a1, b, kp, sms, st);

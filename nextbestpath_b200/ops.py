@@ -3,6 +3,7 @@ CUDA stream to libnbp_b200.so.  PyTorch is plumbing here (device memory, streams
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -110,6 +111,8 @@ def backproject_append(zbuf, R, T, frame_scene, cloud, cloud_len, *, mask=None, 
     n_scenes, cap = cloud.shape[0], cloud.shape[1]
     L = _lib.lib()
     need = L.nbp_backproject_workspace_bytes(n_frames)
+    if gathering_factor < 1.0 and os.environ.get("NBP_BP_KEY_CACHE", "1") != "0":
+        need += L.nbp_backproject_key_cache_bytes(n_frames, H, W)          # every pixel's selection key is evaluated once, not three times
     ws = _ws.get("backproject", need, dev)
     rc = L.nbp_backproject_append(_ptr(zbuf), _ptr(mask), _ptr(R), _ptr(T), _ptr(frame_scene), _ptr(frame_uid),
                                   n_frames, H, W, tan_half_fov(fov_deg), float(fov_range if fov_range else 0.0),
