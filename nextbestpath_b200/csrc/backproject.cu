@@ -17,7 +17,10 @@
 
 namespace nbp {
 
-static constexpr int BP_THREADS = 1024;
+#ifndef NBP_BP_THREADS
+#define NBP_BP_THREADS 512
+#endif
+static constexpr int BP_THREADS = NBP_BP_THREADS;          // 512: two frames per SM overlap each other's barriers and serial sections
 
 struct FrameSel { int32_t n, k; uint32_t tau; int32_t base; int32_t final_len; int32_t pad[3]; };
 
@@ -95,7 +98,7 @@ __device__ __forceinline__ unsigned quad_valid(const BpParams& p, const float* z
 // Per frame: n = number of valid pixels, k = int(n * gf), and -- when k < n -- the k-th smallest key tau of a keyed bijection of the
 // pixel index (radix select, 9-bit digits, shared histogram): exactly k valid pixels have key <= tau.  The first radix pass doubles as
 // the count (n = sum of its histogram); pixels are read four at a time so that four independent Feistel chains are in flight per thread.
-__global__ void __launch_bounds__(BP_THREADS) bp_select(BpParams p) {
+__global__ void __launch_bounds__(BP_THREADS, 2048 / BP_THREADS > 2 ? 2 : 2048 / BP_THREADS) bp_select(BpParams p) {
     __shared__ int s_hist[512];
     __shared__ int s_red[BP_THREADS / 32];
     __shared__ uint32_t s_prefix; __shared__ int s_krem; __shared__ int s_n; __shared__ int s_k;
@@ -161,26 +164,42 @@ __global__ void __launch_bounds__(BP_THREADS) bp_select(BpParams p) {
             if (lane_id() == 0) s_red[threadIdx.x >> 5] = cnt;
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            const int nb = 1 << db;
+        if (threadIdx.x < 32) {
+            // warp 0 scans the histogram: lane l owns bins [l * per, (l + 1) * per) (a 512-iteration loop of one thread was ~10 % of the
+            // kernel: every other warp of the CTA waits for it)
+            const int nb = 1 << db, per = (nb + 31) >> 5;
+            const int b0 = lane_id() * per, b1 = min(nb, b0 + per);
+            int mine = 0;
+            for (int d = b0; d < b1; ++d) mine += s_hist[d];
+            int incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane_id() >= d) incl += t; }
             if (first) {
                 int n = 0;
-                if (subsample) for (int d = 0; d < nb; ++d) n += s_hist[d];
+                if (subsample) n = __shfl_sync(0xffffffffu, incl, 31);
                 else for (int w = 0; w < BP_THREADS / 32; ++w) n += s_red[w];
                 int k = subsample ? (int)((double)n * p.gf) : n;
                 if (k > n) k = n;
                 if (k < 0) k = 0;
-                s_n = n; s_k = k; s_krem = k;
+                if (lane_id() == 0) { s_n = n; s_k = k; s_krem = k; }
+                __syncwarp();
             }
-            if (subsample && s_k > 0 && s_k < s_n) {
-                int krem = s_krem, acc = 0, d = 0;
-                for (; d < nb; ++d) {
-                    if (acc + s_hist[d] >= krem) break;
-                    acc += s_hist[d];
+            const int n_all = s_n, k_all = s_k, krem = s_krem;
+            __syncwarp();
+            if (subsample && k_all > 0 && k_all < n_all) {
+                // the digit d with acc(d) < krem <= acc(d) + hist[d] lies in the first lane whose inclusive sum reaches krem
+                const unsigned reach = __ballot_sync(0xffffffffu, incl >= krem);
+                const int owner = reach ? __ffs(reach) - 1 : 31;
+                if (lane_id() == owner) {
+                    int acc = incl - mine, d = b0;
+                    for (; d < b1; ++d) {
+                        if (acc + s_hist[d] >= krem) break;
+                        acc += s_hist[d];
+                    }
+                    if (d >= nb) d = nb - 1;                  // cannot happen (k <= n)
+                    s_krem = krem - acc;
+                    s_prefix = (prefix << db) | (uint32_t)d;
                 }
-                if (d >= nb) d = nb - 1;                      // cannot happen (k <= n)
-                s_krem = krem - acc;
-                s_prefix = (prefix << db) | (uint32_t)d;
             }
         }
         __syncthreads();
@@ -231,7 +250,7 @@ __device__ __forceinline__ void unproject_store(const BpParams& p, const float* 
     o[2] = fadd(fadd(fmul(dx, sR[6]), fmul(dy, sR[7])), fmul(dz, sR[8]));
 }
 
-__global__ void __launch_bounds__(BP_THREADS) bp_write(BpParams p) {
+__global__ void __launch_bounds__(BP_THREADS, 2048 / BP_THREADS > 2 ? 2 : 2048 / BP_THREADS) bp_write(BpParams p) {
     __shared__ int s_wcnt[BP_THREADS / 32];
     __shared__ float sR[9], sT[3];
     const int f = blockIdx.x;

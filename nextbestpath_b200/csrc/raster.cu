@@ -31,7 +31,7 @@ struct __align__(16) TriRec {          // 24 words
     float z2, d12x, d12y, d20x;        // dIJ = vJ - vI
     float d20y, d01x, d01y, den;       // den = area + 1e-8
     float xmin, xmax, ymin, ymax;      // NDC bbox
-    int face; int pad0, pad1, pad2;
+    int face; float zprune; int pad1, pad2;     // zprune: a lower bound of every depth this triangle can produce (see raster_tiles)
 };
 static_assert(sizeof(TriRec) == 96, "TriRec must be 96 bytes");
 
@@ -108,7 +108,9 @@ __device__ __forceinline__ bool make_record(const V3& a, const V3& b, const V3& 
     r.den = fadd(area, K_EPS);
     r.xmin = fminf(fminf(a.x, b.x), c.x); r.xmax = fmaxf(fmaxf(a.x, b.x), c.x);
     r.ymin = fminf(fminf(a.y, b.y), c.y); r.ymax = fmaxf(fmaxf(a.y, b.y), c.y);
-    r.face = face; r.pad0 = r.pad1 = r.pad2 = 0;
+    r.face = face; r.pad1 = r.pad2 = 0;
+    // the interpolated depth is a convex combination (weights > 0, sum 1 +- a few ulp) of z0, z1, z2 > 0: never below 0.99999 * min z
+    r.zprune = fminf(fminf(a.z, b.z), c.z) * 0.99999f;
     int x0, x1, y0, y1;
     ndc_to_pixel_range(r.xmin, r.xmax, W, H, x0, x1);
     ndc_to_pixel_range(r.ymin, r.ymax, H, W, y0, y1);
@@ -226,6 +228,7 @@ struct TileParams {
     const int32_t* tri_count; const int64_t* tri_off; const uint2* bbox; const TriRec* recs;
     int H, W, tiles_x; float* zbuf; int32_t* pix_to_face;
     int cb, bins_x; const int32_t* bin_count; const uint2* bin_list;
+    int prune;
 };
 
 __global__ void __launch_bounds__(RT_THREADS) raster_tiles(TileParams p) {
@@ -282,6 +285,9 @@ __global__ void __launch_bounds__(RT_THREADS) raster_tiles(TileParams p) {
             const bool cand = (den > 0.0f) ? (e0 > 0.0f && e1 > 0.0f && e2 > 0.0f)
                                            : (e0 < 0.0f && e1 < 0.0f && e2 < 0.0f);
             if (!cand) continue;
+            // a triangle that lies wholly behind the depth already found cannot win (nor tie): skip its six IEEE divisions.  Only valid
+            // for vertex depths > 0 (z_clip > 0): p.prune
+            if (p.prune && best_f >= 0 && r.zprune > best_z) continue;
             const float w0 = fdiv(e0, den), w1 = fdiv(e1, den), w2 = fdiv(e2, den);
             const float z0 = r.z0, z1 = r.z1, z2 = r.z2;
             const float t0 = fmul(fmul(w0, z1), z2);
@@ -369,7 +375,7 @@ extern "C" int nbp_raster_depth_batched(const float* verts, const int32_t* faces
         count_launch();
     }
     const int tiles_x = (W + TILE - 1) / TILE, tiles_y = (H + TILE - 1) / TILE;
-    TileParams tp{tri_count, tri_off, bbox, recs, H, W, tiles_x, zbuf, pix_to_face, cb, bins_x, bin_count, bin_list};
+    TileParams tp{tri_count, tri_off, bbox, recs, H, W, tiles_x, zbuf, pix_to_face, cb, bins_x, bin_count, bin_list, z_clip > 1e-6f ? 1 : 0};
     raster_tiles<<<dim3(tiles_x * tiles_y, n_views), RT_THREADS, 0, st>>>(tp);
     count_launch();
     return check_cuda(cudaGetLastError(), "nbp_raster_depth_batched launch");

@@ -98,39 +98,46 @@ __device__ __forceinline__ void channel_reduce(size_t npix, int C, double* out /
     }
 }
 
-// sum(z) -> acc[0][C]
-__global__ void __launch_bounds__(256) bn_sum_kernel(const __half* __restrict__ z, int ld, int lo, size_t npix, int C, double* acc) {
-    channel_reduce<1>(npix, C, acc, [&](size_t p, int g, float (*a)[8]) {
+// One pass over z: sum(z - s) -> acc[0][C] and sum((z - s)^2) -> acc[1][C] with the per-channel shift s = z[pixel 0] (the first pixel of
+// the tensor: deterministic, and a value of the distribution, so |mean - s| is a few standard deviations at most and the cancellation
+// in var = E[(z-s)^2] - (mean - s)^2 costs a factor (1 + (mean-s)^2/var) on a 1e-7 relative error; partial sums: fp32 over <= ~64
+// pixels per thread, fp64 across threads and blocks).  Round 2 replaced the two sweeps (mean, then squared deviations) by this one.
+__global__ void __launch_bounds__(256) bn_moments_kernel(const __half* __restrict__ z, int ld, int lo, size_t npix, int C, double* acc) {
+    float s[8];
+    ldz(z, 0, ld, lo, threadIdx.x % (C >> 3), s);           // this thread's channel group (as in channel_reduce)
+    channel_reduce<2>(npix, C, acc, [&](size_t p, int g, float (*a)[8]) {
         float f[8];
         ldz(z, p, ld, lo, g, f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[0][j] += f[j];
+        for (int j = 0; j < 8; ++j) { const float d = f[j] - s[j]; a[0][j] += d; a[1][j] = fmaf(d, d, a[1][j]); }
     });
 }
-// sum((z - mean)^2) -> acc[1][C] (mean = acc[0]/npix)
-__global__ void __launch_bounds__(256) bn_sqdev_kernel(const __half* __restrict__ z, int ld, int lo, size_t npix, int C, double* acc) {
-    const double inv = 1.0 / (double)npix;
-    channel_reduce<1>(npix, C, acc + C, [&](size_t p, int g, float (*a)[8]) {
-        float f[8];
-        ldz(z, p, ld, lo, g, f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { const float d = f[j] - (float)(acc[8 * g + j] * inv); a[0][j] = fmaf(d, d, a[0][j]); }
-    });
+
+__device__ __forceinline__ float z_elem(const __half* z, int ld, int lo, int c) {          // element c of pixel 0
+    if (lo < 0) return reinterpret_cast<const float*>(z)[c];
+    return __half2float(z[c]) + __half2float(z[c + lo]) * (1.0f / LO_SCALE);
 }
 
 // batch mean / biased var -> (scale, shift) of the normalisation, invstd, and the running-statistics update
 __global__ void bn_finalize_kernel(const double* acc, size_t npix, int C, const float* gamma, const float* beta,
                                    float* running_mean, float* running_var, float momentum, float eps,
-                                   float* mean, float* invstd, float* scale, float* shift) {
+                                   float* mean, float* invstd, float* scale, float* shift,
+                                   const __half* z0, int ld, int lo) {       // z0 != nullptr: acc holds the moments about z[pixel 0]
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    const double m = acc[c] / (double)npix, var = acc[C + c] / (double)npix;
+    double m = acc[c] / (double)npix, ss = acc[C + c];
+    if (z0) {
+        ss = ss - m * m * (double)npix;                      // sum of squared deviations about the mean
+        if (ss < 0.0) ss = 0.0;
+        m += (double)z_elem(z0, ld, lo, c);
+    }
+    const double var = ss / (double)npix;
     const float is = (float)(1.0 / sqrt(var + (double)eps));
     mean[c] = (float)m; invstd[c] = is;
     const float sc = gamma[c] * is;
     scale[c] = sc; shift[c] = beta[c] - (float)m * sc;
     if (running_mean) {
-        const double unbiased = npix > 1 ? acc[C + c] / (double)(npix - 1) : var;
+        const double unbiased = npix > 1 ? ss / (double)(npix - 1) : var;
         running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)m;
         running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
     }
@@ -672,12 +679,11 @@ extern "C" int nbp_bn_train_stats(const void* z, int ld, int lo, int64_t npix, i
     if (npix <= 0) return invalid("nbp_bn_train_stats: npix must be positive");
     rc = check_cuda(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * C, ST), "memset");
     if (rc) return rc;
-    const size_t smem = sizeof(float) * (size_t)(256 / (C / 8)) * C;
-    bn_sum_kernel<<<red_grid(npix, C), 256, smem, ST>>>(H16(z), ld, lo, (size_t)npix, C, workspace);
-    bn_sqdev_kernel<<<red_grid(npix, C), 256, smem, ST>>>(H16(z), ld, lo, (size_t)npix, C, workspace);
+    const size_t smem = sizeof(float) * 2 * (size_t)(256 / (C / 8)) * C;
+    bn_moments_kernel<<<red_grid(npix, C), 256, smem, ST>>>(H16(z), ld, lo, (size_t)npix, C, workspace);
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(workspace, (size_t)npix, C, gamma, beta, running_mean, running_var, momentum, eps,
-                                                        mean, invstd, scale, shift);
-    count_launch(4);
+                                                        mean, invstd, scale, shift, H16(z), ld, lo);
+    count_launch(3);
     return check_cuda(cudaGetLastError(), "nbp_bn_train_stats launch");
 }
 
@@ -716,7 +722,7 @@ extern "C" int nbp_psi_train(const void* a, int ld_a, int lo_a, int64_t npix, in
     stats1_kernel<<<g, 256, 0, ST>>>(zpsi, (size_t)npix, workspace, 0);
     stats1_kernel<<<g, 256, 0, ST>>>(zpsi, (size_t)npix, workspace, 1);
     bn_finalize_kernel<<<1, 32, 0, ST>>>(workspace, (size_t)npix, 1, gamma1, beta1, running_mean1, running_var1, momentum, eps,
-                                         stat4, stat4 + 1, stat4 + 2, stat4 + 3);
+                                         stat4, stat4 + 1, stat4 + 2, stat4 + 3, nullptr, 0, 0);
     count_launch(5);
     return check_cuda(cudaGetLastError(), "nbp_psi_train launch");
 }

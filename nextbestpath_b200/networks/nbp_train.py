@@ -24,7 +24,7 @@ from . import nbp_model as M
 _DEC_LEVELS = M._DEC_LEVELS
 BN_MOMENTUM, BN_EPS = 0.1, 1e-5
 # training keeps the forward / dgrad accumulation chains short: gradients are ill-conditioned (NBP_TRAIN_K_CHUNK: A/B switch)
-TRAIN_K_CHUNK = int(__import__("os").environ.get("NBP_TRAIN_K_CHUNK", "2"))
+TRAIN_K_CHUNK = int(__import__("os").environ.get("NBP_TRAIN_K_CHUNK", "3"))
 WGRAD_MAX_K_TILES = int(__import__("os").environ.get("NBP_WGRAD_MAX_K_TILES", "0"))     # 0: split K only as far as needed to fill the GPU (bounding the in-TMEM chain showed no accuracy benefit, measured)
 
 
