@@ -16,6 +16,8 @@
 // Arithmetic is pinned op-for-op to oracle/raster_oracle.c (one fp32 rounding per operation, no FMA),
 // so zbuf is bit-identical to the CPU oracle; the min over (z, face) is order-independent, so the
 // non-deterministic append order of kernel 1 does not affect results.
+#include <cstdlib>
+
 #include "nbp_common.cuh"
 
 namespace nbp {
@@ -229,6 +231,7 @@ struct TileParams {
     int H, W, tiles_x; float* zbuf; int32_t* pix_to_face;
     int cb, bins_x; const int32_t* bin_count; const uint2* bin_list;
     int prune;
+    int warp8x4;
 };
 
 __global__ void __launch_bounds__(RT_THREADS) raster_tiles(TileParams p) {
@@ -238,7 +241,11 @@ __global__ void __launch_bounds__(RT_THREADS) raster_tiles(TileParams p) {
     const int view = blockIdx.y;
     const int tile_x = blockIdx.x % p.tiles_x, tile_y = blockIdx.x / p.tiles_x;
     const int px0 = tile_x * TILE, py0 = tile_y * TILE;
-    const int tx = threadIdx.x & (TILE - 1), ty = threadIdx.x >> 4;
+    // a warp covers an 8 x 4 pixel block of the tile (p.warp8x4; 16 x 2 otherwise): the per-triangle box and edge rejections below only
+    // save time when ALL lanes of a warp reject, and a compact footprint is rejected by more triangles than a 16-pixel strip
+    const int wl = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int tx = p.warp8x4 ? ((wi & 1) * 8 + (wl & 7)) : (threadIdx.x & (TILE - 1));
+    const int ty = p.warp8x4 ? ((wi >> 1) * 4 + (wl >> 3)) : (threadIdx.x >> 4);
     const int xi = px0 + tx, yi = py0 + ty;
     const float xf = pix_to_ndc(p.W - 1 - xi, p.W, p.H);
     const float yf = pix_to_ndc(p.H - 1 - yi, p.H, p.W);
@@ -375,7 +382,12 @@ extern "C" int nbp_raster_depth_batched(const float* verts, const int32_t* faces
         count_launch();
     }
     const int tiles_x = (W + TILE - 1) / TILE, tiles_y = (H + TILE - 1) / TILE;
-    TileParams tp{tri_count, tri_off, bbox, recs, H, W, tiles_x, zbuf, pix_to_face, cb, bins_x, bin_count, bin_list, z_clip > 1e-6f ? 1 : 0};
+    TileParams tp{tri_count, tri_off, bbox, recs, H, W, tiles_x, zbuf, pix_to_face, cb, bins_x, bin_count, bin_list, z_clip > 1e-6f ? 1 : 0, 1};
+    {
+        static int w84_env = -1;                             // NBP_RASTER_WARP8X4=0: A/B switch back to 16 x 2 warps
+        if (w84_env < 0) { const char* e = getenv("NBP_RASTER_WARP8X4"); w84_env = e ? atoi(e) : 1; }
+        tp.warp8x4 = w84_env;
+    }
     raster_tiles<<<dim3(tiles_x * tiles_y, n_views), RT_THREADS, 0, st>>>(tp);
     count_launch();
     return check_cuda(cudaGetLastError(), "nbp_raster_depth_batched launch");
