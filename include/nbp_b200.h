@@ -189,6 +189,11 @@ typedef struct nbp_conv_desc {
                                               layer's output never goes to memory.  c_out = 32, 64 or 128 (one n-tile); the whole K reduction
                                               runs as one in-TMEM chain (k_chunk is ignored); not with out_f32 / pool_dst */
     float dot_scale; float dot_shift; int dot_sigmoid;
+    const void* gate_src; int gate_c; int gate_ld; int gate_lo;   /* optional gate on top of the dot epilogue (NULL = off; dot_w required, dot_out
+                                              optional): dst[pixel][dst_c_off + c] = gate_src[pixel][c] * f(dot), c < gate_c -- the tail of
+                                              Attention_block, `x * psi` (nbp_model.py:62), written by the attention GEMM itself in dst_fmt.
+                                              gate_src: NHWC tensor [n][h][w][gate_ld] in the sources' format (`precise`), second plane at gate_lo;
+                                              32-byte aligned, gate_c % 32 == 0 (64 in mode 2); not with up2x */
 } nbp_conv_desc;
 
 /* tcgen05/TMEM/TMA implicit-GEMM convolution: conv_block / up_conv / Attention_block W_g,W_x (nbp_model.py:8-62) */

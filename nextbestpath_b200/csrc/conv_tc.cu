@@ -120,6 +120,9 @@ struct ConvKParams {
     // are contracted with dot_w in fp32 and dot_out[pixel] = f(dot * dot_scale + dot_shift), f = sigmoid or identity.  Fuses the 1-channel
     // 1x1 convolution that follows (Attention_block.psi, Final2) so that its input never goes to memory.
     const float* dot_w; float* dot_out; float dot_scale, dot_shift; int dot_sigmoid;
+    // optional gate on top of the dot epilogue (Attention_block, nbp_model.py:62): dst[pixel][dst_c_off + c] = gate_src[pixel][c] * f(dot),
+    // c < gate_c, written in dst_fmt like a normal output; gate_src is an NHWC tensor in the sources' format (gate_fmt)
+    const __half* gate_src; int gate_c, gate_ld, gate_lo, gate_fmt;
 };
 
 // MODE 0 fp16 | 1 fp16x2 | 2 fp16+e4m3 | 3 fp16+e4m3 with SPLIT stages; HALO = 0: plain stages; 2 | 3: halo stages carrying that many taps.
@@ -456,9 +459,13 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         const int n_chunks = (num_k + p.kchunk - 1) / p.kchunk;
         // dot epilogue: one thread contracts ALL column groups of its pixel (warps of the first column-group set; the others only keep
         // the accumulator hand-shake going): the tile's values stay in registers, no stores, so four warps are plenty
-        const bool dotm = p.dot_out != nullptr;
+        // With a gate every warp contracts the whole tile (the dot is cheap) so that both warps of a lane quarter know the pixel's factor
+        // and share the gate's channel groups.
+        const bool dotm = p.dot_w != nullptr;
+        const bool gatem = p.gate_src != nullptr;
+        const int c_first = (dotm && gatem) ? 0 : cg0;
         const int c_step = dotm ? 1 : EPI_SPLIT;
-        const int c_end = (dotm && cg0 != 0) ? 0 : BLOCK_N / 32;
+        const int c_end = (dotm && !gatem && cg0 != 0) ? 0 : BLOCK_N / 32;
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             float dot = 0.0f;
             const int parity = p.up2x ? (tile & 3) : 0;
@@ -493,6 +500,45 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             const size_t opix = (size_t)((size_t)nn * oh + oy) * ow + ox;
             float* orow_f = reinterpret_cast<float*>(p.dst) + opix * p.dst_ld + p.dst_c_off + n_tile * BLOCK_N;
 
+            // fp32 -> hi plane (fp16) + second plane -> 16-byte stores.  `pix` = first element of the pixel, `ch` = channel of x[0]
+            // inside the pixel, `lo_off` = offset of the second plane; fmt 1: fp16 (x - hi) * 2048 at the same channel index,
+            // fmt 2: per 64-channel group 64 bytes e4m3(x) then 64 bytes e4m3((x - hi) * 2048)
+            auto split_store = [&](__half* pix, int ch, int lo_off, int fmt, const float* x) {
+                uint32_t packed[16];
+                if (PRECISE && fmt == 2) {          // hi plane + e4m3 pair plane (the fp16 lo values are never formed)
+                    uint32_t p8h[8], p8l[8];
+                    bool sat = false;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const __half2 h = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+                        packed[j] = *reinterpret_cast<const uint32_t*>(&h);
+                        const float2 hf = __half22float2(h);
+                        const float r0 = (x[2 * j] - hf.x) * (2048.0f * NBP_E4M3_ACT_SCALE), r1 = (x[2 * j + 1] - hf.y) * (2048.0f * NBP_E4M3_ACT_SCALE);
+                        const uint32_t qh = e4m3x2(x[2 * j] * NBP_E4M3_ACT_SCALE, x[2 * j + 1] * NBP_E4M3_ACT_SCALE);
+                        const uint32_t ql = e4m3x2(r0, r1);
+                        sat |= fmaxf(fabsf(x[2 * j]), fabsf(x[2 * j + 1])) > NBP_E4M3_MAX / NBP_E4M3_ACT_SCALE;
+                        if (j & 1) { p8h[j >> 1] |= qh << 16; p8l[j >> 1] |= ql << 16; } else { p8h[j >> 1] = qh; p8l[j >> 1] = ql; }
+                    }
+                    st_global_v8(pix + ch, packed); st_global_v8(pix + ch + 16, packed + 8);
+                    uint8_t* g = reinterpret_cast<uint8_t*>(pix + lo_off) + (ch >> 6) * 128 + (ch & 63);
+                    st_global_v8(g, p8h); st_global_v8(g + 64, p8l);
+                    if (sat && p.sat_count) atomicAdd(p.sat_count, 1ull);          // rare by construction: out-of-range inputs only
+                    return;
+                }
+                uint32_t packed_lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const __half2 h = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+                    packed[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    if (PRECISE) {
+                        const float2 hf = __half22float2(h);
+                        const __half2 l = __floats2half2_rn((x[2 * j] - hf.x) * 2048.0f, (x[2 * j + 1] - hf.y) * 2048.0f);
+                        packed_lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+                    }
+                }
+                st_global_v8(pix + ch, packed); st_global_v8(pix + ch + 16, packed + 8);
+                if (PRECISE) { st_global_v8(pix + ch + lo_off, packed_lo); st_global_v8(pix + ch + lo_off + 16, packed_lo + 8); }
+            };
             // affine + activation + store of 32 consecutive output channels held as fp32 in v[]
             const float lower = p.relu ? 0.0f : -65504.0f;
             auto finish = [&](int c, const float* v) {
@@ -529,45 +575,6 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                     }
                     return;
                 }
-                // fp32 -> hi plane (fp16) + second plane -> 16-byte stores.  `pix` = first element of the pixel, `ch` = channel of x[0]
-                // inside the pixel, `lo_off` = offset of the second plane; fmt 1: fp16 (x - hi) * 2048 at the same channel index,
-                // fmt 2: per 64-channel group 64 bytes e4m3(x) then 64 bytes e4m3((x - hi) * 2048)
-                auto split_store = [&](__half* pix, int ch, int lo_off, int fmt, const float* x) {
-                    uint32_t packed[16];
-                    if (PRECISE && fmt == 2) {          // hi plane + e4m3 pair plane (the fp16 lo values are never formed)
-                        uint32_t p8h[8], p8l[8];
-                        bool sat = false;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const __half2 h = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
-                            packed[j] = *reinterpret_cast<const uint32_t*>(&h);
-                            const float2 hf = __half22float2(h);
-                            const float r0 = (x[2 * j] - hf.x) * (2048.0f * NBP_E4M3_ACT_SCALE), r1 = (x[2 * j + 1] - hf.y) * (2048.0f * NBP_E4M3_ACT_SCALE);
-                            const uint32_t qh = e4m3x2(x[2 * j] * NBP_E4M3_ACT_SCALE, x[2 * j + 1] * NBP_E4M3_ACT_SCALE);
-                            const uint32_t ql = e4m3x2(r0, r1);
-                            sat |= fmaxf(fabsf(x[2 * j]), fabsf(x[2 * j + 1])) > NBP_E4M3_MAX / NBP_E4M3_ACT_SCALE;
-                            if (j & 1) { p8h[j >> 1] |= qh << 16; p8l[j >> 1] |= ql << 16; } else { p8h[j >> 1] = qh; p8l[j >> 1] = ql; }
-                        }
-                        st_global_v8(pix + ch, packed); st_global_v8(pix + ch + 16, packed + 8);
-                        uint8_t* g = reinterpret_cast<uint8_t*>(pix + lo_off) + (ch >> 6) * 128 + (ch & 63);
-                        st_global_v8(g, p8h); st_global_v8(g + 64, p8l);
-                        if (sat && p.sat_count) atomicAdd(p.sat_count, 1ull);          // rare by construction: out-of-range inputs only
-                        return;
-                    }
-                    uint32_t packed_lo[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const __half2 h = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
-                        packed[j] = *reinterpret_cast<const uint32_t*>(&h);
-                        if (PRECISE) {
-                            const float2 hf = __half22float2(h);
-                            const __half2 l = __floats2half2_rn((x[2 * j] - hf.x) * 2048.0f, (x[2 * j + 1] - hf.y) * 2048.0f);
-                            packed_lo[j] = *reinterpret_cast<const uint32_t*>(&l);
-                        }
-                    }
-                    st_global_v8(pix + ch, packed); st_global_v8(pix + ch + 16, packed + 8);
-                    if (PRECISE) { st_global_v8(pix + ch + lo_off, packed_lo); st_global_v8(pix + ch + lo_off + 16, packed_lo + 8); }
-                };
                 if (valid) split_store(p.dst + opix * p.dst_ld, p.dst_c_off + n_tile * BLOCK_N + c * 32, p.dst_lo_off, p.dst_fmt, a);
                 if (p.pool) {
                     // fused nn.MaxPool2d(2,2): the 2x2 window of a pixel lives in lanes {l, l^1, l^tw, l^(tw+1)} of this warp (tile rows
@@ -611,16 +618,53 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS);
 #pragma unroll 1
-                for (int c = cg0; c < c_end; c += c_step) {
+                for (int c = c_first; c < c_end; c += c_step) {
                     float v[32];
                     load_group(t_row, c, v);
                     finish(c, v);
                 }
                 release();
-                if (dotm && cg0 == 0 && valid) {
+                if (dotm) {
                     float z = fmaf(dot, p.dot_scale, p.dot_shift);
                     if (p.dot_sigmoid) z = 1.0f / (1.0f + expf(-z));
-                    p.dot_out[opix] = z;
+                    if (p.dot_out && cg0 == 0 && valid) p.dot_out[opix] = z;
+                    if (gatem && valid) {
+                        // this pixel's gate_c channels times z, 32 channels at a time, alternate groups per warp of the lane quarter
+                        const __half* xp = p.gate_src + opix * p.gate_ld;
+                        for (int gg = cg0; gg < p.gate_c / 32; gg += EPI_SPLIT) {
+                            uint32_t h[16];
+                            ld_global_nc_v8(xp + gg * 32, h); ld_global_nc_v8(xp + gg * 32 + 16, h + 8);
+                            float x[32];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+                                x[2 * j] = t.x; x[2 * j + 1] = t.y;
+                            }
+                            if (PRECISE && p.gate_fmt == 2) {       // second plane: 64 e4m3(x / 8) bytes, then 64 e4m3((x - hi) * 2048 / 8) bytes per 64 channels
+                                uint32_t q[8];
+                                ld_global_nc_v8(reinterpret_cast<const uint8_t*>(xp + p.gate_lo) + (gg >> 1) * 128 + 64 + (gg & 1) * 32, q);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    uint32_t h2;
+                                    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"((uint16_t)(q[j >> 1] >> (16 * (j & 1)))));
+                                    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+                                    x[2 * j] = fmaf(t.x, 1.0f / (2048.0f * NBP_E4M3_ACT_SCALE), x[2 * j]);
+                                    x[2 * j + 1] = fmaf(t.y, 1.0f / (2048.0f * NBP_E4M3_ACT_SCALE), x[2 * j + 1]);
+                                }
+                            } else if (PRECISE) {
+                                uint32_t l[16];
+                                ld_global_nc_v8(xp + p.gate_lo + gg * 32, l); ld_global_nc_v8(xp + p.gate_lo + gg * 32 + 16, l + 8);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&l[j]));
+                                    x[2 * j] = fmaf(t.x, 1.0f / 2048.0f, x[2 * j]); x[2 * j + 1] = fmaf(t.y, 1.0f / 2048.0f, x[2 * j + 1]);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) x[j] = fminf(fmaxf(x[j] * z, -65504.0f), 65504.0f);
+                            split_store(p.dst + opix * p.dst_ld, p.dst_c_off + gg * 32, p.dst_lo_off, p.dst_fmt, x);
+                        }
+                    }
                 }
             } else {
                 // long reductions: every K chunk is summed inside TMEM (truncating accumulator), the chunks are summed here
@@ -777,10 +821,21 @@ using namespace nbp;
 
 extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     if (!d) return invalid("nbp_conv_fwd: null descriptor");
-    const bool dotm = d->dot_out != nullptr;
+    const bool dot_any = d->dot_out != nullptr || d->gate_src != nullptr;   // dot epilogue requested
+    const bool gate = d->gate_src != nullptr;
+    const bool dotm = dot_any && !gate;                                      // dot epilogue that writes no activation: dst is unused
     if (!d->src0 || !d->weight || !d->scale || !d->shift || (!d->dst && !dotm)) return invalid("nbp_conv_fwd: null pointer in descriptor");
-    if (dotm && (!d->dot_w || d->out_f32 || d->pool_dst || (d->c_out != 32 && d->c_out != 64 && d->c_out != 128) || ((uintptr_t)d->dot_w & 15)))
+    if (dot_any && (!d->dot_w || d->out_f32 || d->pool_dst || (d->c_out != 32 && d->c_out != 64 && d->c_out != 128) || ((uintptr_t)d->dot_w & 15)))
         return invalid("nbp_conv_fwd: the dot epilogue needs dot_w (16-byte aligned), c_out = 32, 64 or 128 (one n-tile; got %d), no fp32 / pooled output", d->c_out);
+    if (gate) {
+        const int gfmt = d->precise;                                          // the gate source is in the sources' format
+        if (d->up2x || d->gate_c <= 0 || d->gate_c % 32 || d->gate_ld % 16 || ((uintptr_t)d->gate_src & 31) ||
+            (gfmt && (d->gate_lo < d->gate_c || d->gate_lo % 16 || d->gate_lo + d->gate_c > d->gate_ld)) || (!gfmt && d->gate_c > d->gate_ld) ||
+            (gfmt == 2 && (d->gate_lo % 64 || d->gate_c % 64)))
+            return invalid("nbp_conv_fwd: bad gate source layout c=%d ld=%d lo=%d (32-byte pieces; e4m3 pair planes in 64-channel groups; not with up2x)",
+                           d->gate_c, d->gate_ld, d->gate_lo);
+    }
+    const int c_written = gate ? d->gate_c : d->c_out;                       // channels the epilogue stores per pixel
     if (d->taps != 1 && d->taps != 9 && !(d->taps == 4 && d->up2x)) return invalid("nbp_conv_fwd: taps must be 1 or 9, or 4 with up2x (got %d)", d->taps);
     if (d->up2x && d->taps != 4) return invalid("nbp_conv_fwd: up2x needs the 4-tap parity weights");
     if (d->n <= 0 || d->h <= 0 || d->w <= 0) return invalid("nbp_conv_fwd: bad image dims n=%d h=%d w=%d", d->n, d->h, d->w);
@@ -798,12 +853,12 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
         return invalid("nbp_conv_fwd: e4m3 pair planes need 64-channel aligned plane offsets");
     const int span0 = precise ? d->lo0 + d->c0 : d->c0, span1 = precise ? d->lo1 + d->c1 : d->c1;
     if (precise && (d->lo0 < d->c0 || d->lo0 % 8 || (d->c1 > 0 && (d->lo1 < d->c1 || d->lo1 % 8)) ||
-                    (!d->out_f32 && !dotm && (d->dst_lo_off < d->c_out || d->dst_lo_off % 8))))
+                    (!d->out_f32 && !dotm && (d->dst_lo_off < c_written || d->dst_lo_off % 8))))
         return invalid("nbp_conv_fwd: lo-plane offsets must be >= the channel count and multiples of 8");
     if (d->ld0 < span0 || d->ld0 % 8 || (d->c1 > 0 && (d->ld1 < span1 || d->ld1 % 8)))
         return invalid("nbp_conv_fwd: source pixel strides must cover the planes and be multiples of 8");
     if (d->c_out <= 0 || d->c_out % 32) return invalid("nbp_conv_fwd: c_out must be a positive multiple of 32 (got %d)", d->c_out);
-    if (!dotm && (d->dst_ld % 8 || d->dst_c_off % 8 || d->dst_c_off + ((precise && !d->out_f32) ? d->dst_lo_off : 0) + d->c_out > d->dst_ld))
+    if (!dotm && (d->dst_ld % 8 || d->dst_c_off % 8 || d->dst_c_off + ((precise && !d->out_f32) ? d->dst_lo_off : 0) + c_written > d->dst_ld))
         return invalid("nbp_conv_fwd: bad destination channel layout ld=%d off=%d lo_off=%d c_out=%d", d->dst_ld, d->dst_c_off, d->dst_lo_off, d->c_out);
     if (((uintptr_t)d->src0 | (uintptr_t)d->src1 | (uintptr_t)d->weight) & 15)
         return invalid("nbp_conv_fwd: source and weight pointers must be 16-byte aligned");
@@ -878,13 +933,14 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
         // 8 + 1 makes the epilogue warps fold two chunks per tile for nothing (measured -3..-13 % on those layers); spreading
         // longer reductions evenly (18 as 6+6+6 instead of 8+8+2) was measured slower and is not done.
         if (precise && want > 0 && total > kp.kchunk && total / smult * kp.gtaps <= want + want / 4) kp.kchunk = total;
-        if (dotm) kp.kchunk = total;              // the dot epilogue contracts one whole accumulator per tile
+        if (dot_any) kp.kchunk = total;           // the dot epilogue contracts one whole accumulator per tile
     }
     kp.b_rows_per_parity = (precise ? 2 : 1) * d->c_out;
     kp.scale = d->scale; kp.shift = d->shift; kp.relu = d->relu;
     kp.dst = (__half*)d->dst; kp.dst_ld = d->dst_ld; kp.dst_c_off = d->dst_c_off; kp.dst_lo_off = d->dst_lo_off;
     kp.pool = (__half*)d->pool_dst; kp.pool_ld = d->pool_ld; kp.pool_lo_off = d->pool_lo_off;
-    kp.dot_w = d->dot_w; kp.dot_out = d->dot_out; kp.dot_scale = d->dot_scale; kp.dot_shift = d->dot_shift; kp.dot_sigmoid = d->dot_sigmoid ? 1 : 0;
+    kp.dot_w = dot_any ? d->dot_w : nullptr; kp.dot_out = d->dot_out; kp.dot_scale = d->dot_scale; kp.dot_shift = d->dot_shift; kp.dot_sigmoid = d->dot_sigmoid ? 1 : 0;
+    kp.gate_src = (const __half*)d->gate_src; kp.gate_c = d->gate_c; kp.gate_ld = d->gate_ld; kp.gate_lo = d->gate_lo; kp.gate_fmt = d->precise;
     if (d->pool_dst) {
         if (d->up2x || d->out_f32) return invalid("nbp_conv_fwd: pool_dst cannot be combined with up2x / out_f32");
         if ((d->h | d->w) & 1) return invalid("nbp_conv_fwd: pool_dst needs even h and w (got %d x %d)", d->h, d->w);

@@ -211,6 +211,10 @@ __device__ __forceinline__ void ld_shared_f32x4(uint32_t addr, float* v) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
 }
 // One 32-byte global store per thread (STG.256, sm_100+): a full L2 sector per request.  `ptr` must be 32-byte aligned.
+__device__ __forceinline__ void ld_global_nc_v8(const void* ptr, uint32_t* r) {      // 32-byte read-only load (one L2 sector)
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(ptr));
+}
 __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t* r) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  :: "l"(ptr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");

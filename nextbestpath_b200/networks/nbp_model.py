@@ -171,6 +171,10 @@ def _affine(sd, conv, bn, eps=1e-5):
 LO_SCALE = 2048.0
 # A/B switch (NBP_FUSE_DOT=0): psi of the attention gates and the Final2 head as separate kernels instead of the conv kernel's dot epilogue
 FUSE_DOT = os.environ.get("NBP_FUSE_DOT", "1") != "0"
+# x * psi written by the attention GEMM's epilogue too (nbp_conv_desc.gate_src; needs FUSE_DOT).  Built, tested, and OFF: measured on B200
+# it is a wash (8.71-8.81 ms per 32-scene forward without, 8.68-8.90 with) -- the thread-per-pixel epilogue reads and writes the skip
+# tensor in 32-byte pieces, which costs what the coalesced streaming kernel it replaces cost
+FUSE_GATE = os.environ.get("NBP_FUSE_GATE", "0") != "0"
 
 
 def _pack_gemm_weight(w2d, precise):
@@ -312,9 +316,10 @@ class _Act:
         return _Act(self.t, c, self.ld, self.lo, self.h, self.w, self.off + off, self.fmt)
 
 
-def _conv(pk, layer, B, src0, taps, dst, relu=True, src1=None, up2x=False, k_chunk=0, pool=None, dot=None):
-    """``dot`` = (w [c_out] fp32, scale, shift, sigmoid, out fp32 [B,h,w]): the dot epilogue of nbp_conv_desc -- the layer's output is
-    contracted with ``w`` per pixel instead of being stored (``dst`` is None then)."""
+def _conv(pk, layer, B, src0, taps, dst, relu=True, src1=None, up2x=False, k_chunk=0, pool=None, dot=None, gate=None):
+    """``dot`` = (w [c_out] fp32, scale, shift, sigmoid, out fp32 [B,h,w] or None): the dot epilogue of nbp_conv_desc -- the layer's output
+    is contracted with ``w`` per pixel instead of being stored (``dst`` is None then).  ``gate`` (an _Act in the sources' format, with
+    ``dot``): ``dst`` receives gate * f(dot) instead (Attention_block's x * psi)."""
     mode = layer.get("mode", 1 if pk["precise"] else 0)
     if mode and (src0.fmt != mode or (src1 is not None and src1.fmt != mode)):
         raise RuntimeError(f"conv in mode {mode} got sources in format {src0.fmt}" + (f"/{src1.fmt}" if src1 is not None else ""))
@@ -327,8 +332,10 @@ def _conv(pk, layer, B, src0, taps, dst, relu=True, src1=None, up2x=False, k_chu
                       dst.lo if dst is not None else 0, 0, k_chunk,
                       (dst.fmt if mode else 0) if dst is not None else 0, (pool.fmt if pool is not None else 0) if mode else 0, layer.get("lo_scale", 1.0 / LO_SCALE),
                       pk["sat_count"].data_ptr() if "sat_count" in pk else None, pool.ptr if pool is not None else None, pool.ld if pool is not None else 0, pool.lo if pool is not None else 0,
-                      dot[0].data_ptr() if dot is not None else None, dot[4].data_ptr() if dot is not None else None,
-                      dot[1] if dot is not None else 0.0, dot[2] if dot is not None else 0.0, (1 if dot[3] else 0) if dot is not None else 0)
+                      dot[0].data_ptr() if dot is not None else None, dot[4].data_ptr() if dot is not None and dot[4] is not None else None,
+                      dot[1] if dot is not None else 0.0, dot[2] if dot is not None else 0.0, (1 if dot[3] else 0) if dot is not None else 0,
+                      gate.ptr if gate is not None else None, gate.c if gate is not None else 0, gate.ld if gate is not None else 0,
+                      gate.lo if gate is not None else 0)
     _lib.check(_lib.lib().nbp_conv_fwd(ctypes.byref(d), _stream()), "nbp_conv_fwd")
 
 
@@ -432,7 +439,11 @@ def _forward_eval(pk, x, out1, out2, vmax):
         _conv(pk, pk[f"Up{t}"], B, d, 4, g, up2x=True)   # upsample fused: d is read at its own (half) resolution
         att = pk[f"Att{t}"]
         gated = cat.channels(0, f_l)
-        if FUSE_DOT and att["c_out"] <= 128:
+        if FUSE_GATE and FUSE_DOT and att["c_out"] <= 128:
+            # the whole gate in the attention GEMM's epilogue: psi = sigmoid(BN(w_psi . a)) (dot epilogue) and x * psi written into the
+            # concat buffer by the same threads; neither `a` nor psi go to memory and the skip tensor is read once (TMA) + once from L2
+            _conv(pk, att, B, g, 1, gated, relu=True, src1=skip, dot=(att["w_psi"], att["psi_scale"], att["psi_shift"], True, None), gate=skip)
+        elif FUSE_DOT and att["c_out"] <= 128:
             # psi = sigmoid(BN(w_psi . a)) leaves the attention GEMM's epilogue directly (dot epilogue): `a` never goes to memory
             psi = torch.empty((B, skip.h, skip.w), dtype=torch.float32, device=dev)
             _conv(pk, att, B, g, 1, None, relu=True, src1=skip, dot=(att["w_psi"], att["psi_scale"], att["psi_shift"], True, psi))
