@@ -24,8 +24,8 @@ cpu_baseline: the oracle (CPU restatement of the reference path; the reference's
 extra blocks (reported baselines / secondary configs, each outside the two timed regions above):
   latency_b1     : NBP.forward at batch 1 (BASELINE configs[0]: the reference calls the net with one scene), 128^2 and 256^2
   cudnn_baseline : the same network under torch + cuDNN on this GPU (fp32 with TF32 off, and TF32 on), "the kernel to beat"
-  configs3_reduced: BASELINE configs[3] shape (AiMDoom-insane-shaped meshes, 512x512 grid) at 8 rollouts per GPU; at N = 4 ranks the
-                   block runs the full configuration (32 per GPU = 128 rollouts across 4 GPUs)
+  configs3_reduced: BASELINE configs[3] shape (AiMDoom-insane-shaped meshes, 512x512 grid) at 32 rollouts per GPU: one GPU's share of the
+                   configuration; at N = 4 ranks the block IS configs[3] (128 rollouts across 4 GPUs)
   train          : BASELINE configs[2] shape -- NBP fwd + loss + bwd + AdamW on 256^2 tiles, 64 tiles per GPU per optimizer
                    step, NCCL all-reduce of the flat gradient across the N ranks
 """
@@ -524,11 +524,11 @@ def cudnn_baseline(net, dev, B_total, S, chunk, our_value):
 
 
 def cfg3_block(args, dev, world, rank, net, max_over_ranks, barrier):
-    """BASELINE configs[3] shape at reduced scene count: AiMDoom-insane-shaped meshes (~50 k triangles), 512x512 grid, 8 rollouts per
-    GPU (the full configuration is 128 rollouts across 4 GPUs = 32 per GPU; 8 scenes at 512^2 are one network chunk, the same tensor
-    sizes as 32 scenes at 256^2).  Same engine, same network module (its graph for the new shape is captured in the warm-up)."""
+    """BASELINE configs[3] per-GPU share: AiMDoom-insane-shaped meshes (~50 k triangles), 512x512 grid, 32 rollouts per GPU (the full
+    configuration is 128 rollouts across 4 GPUs = 32 per GPU; the network runs them in chunks of 8 scenes: 8 scenes at 512^2 have the
+    tensor sizes of 32 scenes at 256^2).  Same engine, same network module (its graph for the new shape is captured in the warm-up)."""
     from nextbestpath_b200.rollout import RolloutEngine
-    n_sc, prefill, warm, steps, S = (32 if world == 4 else 8), 20, 2, 3, 512      # 4 ranks: the full configs[3] (128 rollouts across 4 GPUs)
+    n_sc, prefill, warm, steps, S = 32, 20, 2, 3, 512     # 32 rollouts per GPU: at 4 ranks exactly configs[3] (128 rollouts across 4 GPUs)
     old_chunk, net.max_chunk = net.max_chunk, 8                                   # 8 scenes at 512^2 = the tensor sizes of 32 scenes at 256^2
     scenes, poses, az = make_workload(n_sc, "insane", prefill + warm + steps + 4, rank0_scene_index=rank * n_sc, seed0=5000)
     eng = RolloutEngine(scenes, net, dev, S=S, max_steps=prefill + warm + steps + 3, seed=9)

@@ -33,7 +33,7 @@ __device__ __forceinline__ int point_cell(float x, float y, float z, float cx, f
                                           int n_pieces, int S, float lo, float scale) {
     int slab = -1;
 #pragma unroll
-    for (int q = 0; q < SC_MAX_BOUNDS; ++q) slab += (q < nb && y > b[q]) ? 1 : 0;     // bucketize(right=False) - 1
+    for (int q = 0; q < SC_MAX_BOUNDS; ++q) slab += (y > b[q]) ? 1 : 0;     // bucketize(right=False) - 1; b[q >= nb] = +inf (set by the callers)
     if (slab < 0 || slab >= n_pieces) return -1;
     const float r = cell_coord(-fsub(z, cz), lo, scale);      // rows <- -(z - c_z)
     const float c = cell_coord(-fsub(x, cx), lo, scale);      // cols <- -(x - c_x)
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(SC_THREADS) grid_scatter(ScatterParams p) {
     __shared__ float s_c[2];
     __shared__ int s_nb;
     if (threadIdx.x < SC_MAX_BOUNDS)
-        s_b[threadIdx.x] = threadIdx.x < p.max_bounds ? p.bounds[(size_t)scene * p.max_bounds + threadIdx.x] : 0.0f;
+        s_b[threadIdx.x] = (int)threadIdx.x < min(p.n_bounds[scene], p.max_bounds) ? p.bounds[(size_t)scene * p.max_bounds + threadIdx.x] : INFINITY;
     if (threadIdx.x == 0) {
         s_c[0] = p.pose[scene * 5 + 0]; s_c[1] = p.pose[scene * 5 + 2];
         s_nb = min(p.n_bounds[scene], p.max_bounds);
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(SH_THREADS) grid_scatter_hash(ScatterParams p)
     __shared__ float s_c[2];
     __shared__ int s_nb;
     if (threadIdx.x < SC_MAX_BOUNDS)
-        s_b[threadIdx.x] = threadIdx.x < p.max_bounds ? p.bounds[(size_t)scene * p.max_bounds + threadIdx.x] : 0.0f;
+        s_b[threadIdx.x] = (int)threadIdx.x < min(p.n_bounds[scene], p.max_bounds) ? p.bounds[(size_t)scene * p.max_bounds + threadIdx.x] : INFINITY;
     if (threadIdx.x == 0) {
         s_c[0] = p.pose[scene * 5 + 0]; s_c[1] = p.pose[scene * 5 + 2];
         s_nb = min(p.n_bounds[scene], p.max_bounds);
@@ -140,9 +140,9 @@ __global__ void __launch_bounds__(SH_THREADS) grid_scatter_hash(ScatterParams p)
     const float4* src = reinterpret_cast<const float4*>(p.cloud + (size_t)scene * (size_t)p.cap * 3);
     const int n_groups = (n + 3) / 4;
     const int n_chunks = (n_groups + SH_CHUNK_GROUPS - 1) / SH_CHUNK_GROUPS;
+    if ((int)blockIdx.x < n_chunks) for (int i = threadIdx.x; i < SH_SLOTS; i += SH_THREADS) { keys[i] = -1; cnts[i] = 0; }
+    __syncthreads();
     for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-        for (int i = threadIdx.x; i < SH_SLOTS; i += SH_THREADS) { keys[i] = -1; cnts[i] = 0; }
-        __syncthreads();
         const int g1 = min(n_groups, (chunk + 1) * SH_CHUNK_GROUPS);
         for (int gi = chunk * SH_CHUNK_GROUPS + threadIdx.x; gi < g1; gi += SH_THREADS) {
             const float4 a = __ldcs(src + 3 * (size_t)gi), bq = __ldcs(src + 3 * (size_t)gi + 1), c = __ldcs(src + 3 * (size_t)gi + 2);
@@ -165,9 +165,9 @@ __global__ void __launch_bounds__(SH_THREADS) grid_scatter_hash(ScatterParams p)
             }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < SH_SLOTS; i += SH_THREADS) {
+        for (int i = threadIdx.x; i < SH_SLOTS; i += SH_THREADS) {              // flush, and leave the slot empty for the next chunk
             const int key = keys[i];
-            if (key >= 0) atomicAdd(g + key, (float)cnts[i]);
+            if (key >= 0) { atomicAdd(g + key, (float)cnts[i]); keys[i] = -1; cnts[i] = 0; }
         }
         __syncthreads();
     }
