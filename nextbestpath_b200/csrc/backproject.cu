@@ -98,7 +98,7 @@ __device__ __forceinline__ unsigned quad_valid(const BpParams& p, const float* z
 // Per frame: n = number of valid pixels, k = int(n * gf), and -- when k < n -- the k-th smallest key tau of a keyed bijection of the
 // pixel index (radix select, 9-bit digits, shared histogram): exactly k valid pixels have key <= tau.  The first radix pass doubles as
 // the count (n = sum of its histogram); pixels are read four at a time so that four independent Feistel chains are in flight per thread.
-__global__ void __launch_bounds__(BP_THREADS, 2048 / BP_THREADS > 2 ? 2 : 2048 / BP_THREADS) bp_select(BpParams p) {
+__global__ void __launch_bounds__(BP_THREADS, BP_THREADS <= 512 ? 2 : 1) bp_select(BpParams p) {
     __shared__ int s_hist[512];
     __shared__ int s_red[BP_THREADS / 32];
     __shared__ uint32_t s_prefix; __shared__ int s_krem; __shared__ int s_n; __shared__ int s_k;
@@ -250,7 +250,7 @@ __device__ __forceinline__ void unproject_store(const BpParams& p, const float* 
     o[2] = fadd(fadd(fmul(dx, sR[6]), fmul(dy, sR[7])), fmul(dz, sR[8]));
 }
 
-__global__ void __launch_bounds__(BP_THREADS, 2048 / BP_THREADS > 2 ? 2 : 2048 / BP_THREADS) bp_write(BpParams p) {
+__global__ void __launch_bounds__(BP_THREADS, BP_THREADS <= 512 ? 2 : 1) bp_write(BpParams p) {
     __shared__ int s_wcnt[BP_THREADS / 32];
     __shared__ float sR[9], sT[3];
     const int f = blockIdx.x;
