@@ -52,7 +52,7 @@ __device__ __forceinline__ void ld8f(const float* p, float* f);
 // The raw conv output z feeds BatchNorm (statistics, normalisation, backward).  It is stored either as a split fp16x2 tensor
 // (lo >= 0) or -- train mode, same 4 bytes per element -- as plain fp32 (lo < 0, row stride ld floats): with 22 significant bits
 // the cancellation in (z - mean) flips ReLU / max-pool decisions that the fp32 reference takes the other way, which is what
-// dominated the whole-network gradient error (scripts/gradient_study.py).
+// dominated the whole-network gradient error (tests/studies/gradient_study.py).
 __device__ __forceinline__ void ldz(const __half* z, size_t pix, int ld, int lo, int g, float* f) {
     if (lo < 0) ld8f(reinterpret_cast<const float*>(z) + pix * (size_t)ld + 8 * g, f);
     else ld8(z + pix * (size_t)ld + 8 * g, lo, f);

@@ -89,7 +89,7 @@ class _ZF32:
     """The raw pre-BatchNorm tensor z as plain fp32 NHWC (same 4 bytes per element as the split fp16x2 format).  BatchNorm subtracts
     the batch mean from z: with the 22 significant bits of fp16x2 that cancellation flips ReLU / max-pool decisions the fp32
     reference takes the other way, and those flips -- not the GEMM precision -- dominated the whole-network gradient error
-    (scripts/gradient_study.py: 4.2e-3 -> 5.5e-5 at B=2, S=128).  The kernels take it through the `lo < 0` convention."""
+    (tests/studies/gradient_study.py: 4.2e-3 -> 5.5e-5 at B=2, S=128).  The kernels take it through the `lo < 0` convention."""
 
     __slots__ = ("t", "c", "ld", "lo", "h", "w")
 

@@ -13,7 +13,7 @@ import torch.distributed as dist
 from nextbestpath_b200.networks import NBP
 from nextbestpath_b200.train import FlatGradAllReduce, train_step
 from nextbestpath_b200 import ops
-from oracle import nbp_torch as NT       # seeded weights / synthetic count images only
+from nextbestpath_b200 import synthetic as syn    # seeded weights / synthetic count images come from the product package
 
 
 def main():
@@ -26,7 +26,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    net = NBP(); net.load_state_dict(NT.golden_state_dict(seed=9)); net.to(dev)
+    net = NBP(); net.load_state_dict(syn.seeded_nbp_state_dict(net, 9)); net.to(dev)
     opt = torch.optim.AdamW(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)    # nbp_utils.py:228
     red = FlatGradAllReduce(net.parameters())
     S, K = a.grid, 64
@@ -34,7 +34,7 @@ def main():
     mbs = []
     for i in range(0, a.tiles, a.micro):
         b = min(a.micro, a.tiles - i)
-        x = NT.count_like_input(b, S, seed=100 * rank + i).to(dev)
+        x = syn.count_like_input(b, S, seed=100 * rank + i).to(dev)
         tp = torch.stack((torch.randint(0, 8, (b, K), generator=g), torch.randint(0, S // 4, (b, K), generator=g),
                           torch.randint(0, S // 4, (b, K), generator=g)), -1).to(dev)
         mbs.append((x, tp, (torch.rand(b, K, generator=g) * 10).to(dev), (torch.rand(b, 1, S, S, generator=g) < 0.2).float().to(dev)))

@@ -4,14 +4,14 @@ import sys, os, time, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nextbestpath_b200.networks import NBP
 from nextbestpath_b200.train import sparse_value_loss
-from oracle import nbp_torch as NT
+from nextbestpath_b200 import synthetic as syn    # seeded weights / synthetic count images come from the product package
 dev = torch.device("cuda", 0)
-net = NBP(); net.load_state_dict(NT.golden_state_dict(seed=9)); net.to(dev).train()
+net = NBP(); net.load_state_dict(syn.seeded_nbp_state_dict(net, 9)); net.to(dev).train()
 opt = torch.optim.AdamW(net.parameters(), lr=1e-3)
 S, K, b = 256, 64, int(sys.argv[1]) if len(sys.argv) > 1 else 16
 g = torch.Generator().manual_seed(0)
 def mb(i):
-    x = NT.count_like_input(b, S, seed=i).to(dev)
+    x = syn.count_like_input(b, S, seed=i).to(dev)
     tp = torch.stack((torch.randint(0, 8, (b, K), generator=g), torch.randint(0, S // 4, (b, K), generator=g), torch.randint(0, S // 4, (b, K), generator=g)), -1).to(dev)
     return (x, tp, (torch.rand(b, K, generator=g) * 10).to(dev), (torch.rand(b, 1, S, S, generator=g) < 0.2).float().to(dev))
 mbs = [mb(i) for i in range(4)]

@@ -9,15 +9,15 @@ Here the network runs in float64 with explicit rounding at exactly those storage
     A  operands of the forward convs (activations / weights)        Z  storage of the raw conv output z (read by BatchNorm fwd + bwd)
     G  dz as the operand of dgrad / wgrad                            F  fp32 results of dgrad / wgrad and fp32 gradients between layers
 
-Tensor-core accumulation error is not modelled.  Usage: python scripts/gradient_study.py [B] [S]"""
+Tensor-core accumulation error is not modelled.  Usage: python tests/studies/gradient_study.py [B] [S]"""
 import os
 import sys
 
 import torch
 import torch.nn.functional as F
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 from oracle import nbp_torch as NT
 
 

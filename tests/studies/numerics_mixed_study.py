@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """CPU emulation of the mixed numeric mode (which layers keep fp16x2, every other GEMM layer = fp16 hi product + e4m3 corrections):
 value-map / obstacle-map error against the fp32 oracle.  Planning aid for NBP.full_precision_layers; results in profiles/r02_numerics_mixed.txt.
-Usage: python scripts/numerics_mixed_study.py S seed [seed ...]"""
+Usage: python tests/studies/numerics_mixed_study.py S seed [seed ...]"""
 import os, sys, torch, torch.nn.functional as F
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import nbp_torch as NT
 LO = 2048.0
 def q8(x): return x.clamp(-448, 448).to(torch.float8_e4m3fn).float()

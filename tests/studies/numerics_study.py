@@ -15,14 +15,14 @@ value-map / obstacle-map error against the fp32 oracle of cheaper schemes:
                 channels, for activations and weights) -> 2 pass-equivalents
 
 Products are formed in fp32 on the CPU (F.conv2d), i.e. accumulation error is NOT modelled (the kernel's chunked accumulation
-keeps it below the operand error).  Usage: python scripts/numerics_study.py [S] [seeds...]"""
+keeps it below the operand error).  Usage: python tests/studies/numerics_study.py [S] [seeds...]"""
 import os
 import sys
 
 import torch
 import torch.nn.functional as F
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import nbp_torch as NT
 
 LO = 2048.0
