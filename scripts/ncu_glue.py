@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Non-GEMM network kernels of the LAST forward in `ncu --csv --metrics gpu__time_duration.sum,dram__bytes.sum` logs of scripts/profile_forward.py."""
 import csv, collections, sys
-N_GLUE = 10          # conv_first, 6 attention gates, 2 heads (+ the fused heading max inside head<8>) per forward
+N_GLUE = 10          # conv_first, att_gate launches (6: four nbp_att_scale + two level-5 gates), head<8> per forward
 def load(path):
     rows = list(csv.reader(open(path, errors="ignore")))
     hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]; h = rows[hi]

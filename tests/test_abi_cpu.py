@@ -56,3 +56,13 @@ def test_conv_desc_layout_matches_the_header(tmp_path):
     d.n = 1; d.h = 16; d.w = 16; d.taps = 1; d.c_out = 256; d.dot_out = 64; d.dot_w = 64
     rc = _lib.lib().nbp_conv_fwd(ctypes.byref(d), None)
     assert rc == -1 and b"dot epilogue" in _lib.lib().nbp_last_error()
+
+
+def test_workspace_size_queries():
+    """Size queries are pure host arithmetic: the back-projection key scratch holds 4 bytes per pixel and frame on top of the
+    selection records, and the combined workspace is what ops.backproject_append allocates for the sub-sampling path."""
+    L = _lib.lib()
+    base = L.nbp_backproject_workspace_bytes(1024)
+    keys = L.nbp_backproject_key_cache_bytes(1024, 256, 456)
+    assert base >= 32 * 1024 and 4 * 1024 * 256 * 456 <= keys <= 4 * 1024 * 256 * 456 + 512
+    assert L.nbp_backproject_key_cache_bytes(-1, 256, 456) == 0 and L.nbp_backproject_key_cache_bytes(4, 0, 456) == 0
