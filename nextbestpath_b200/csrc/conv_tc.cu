@@ -30,12 +30,14 @@
 // conv's zero padding.  Channel concatenation (torch.cat((skip*psi, up), 1), nbp_model.py:128) is fused by
 // walking two source tensors inside the K loop.
 //
-// Warp roles (256 threads, 1 CTA / SM, persistent over tiles):
-//   warp 0 : TMA producer (one elected lane)      smem ring of STAGES x {A 16 KB, B BLOCK_N*128 B}
-//   warp 1 : tcgen05.mma issuer (one elected lane) 4 x (128 x BLOCK_N x 16) UMMAs per stage
-//   warp 2 : TMEM allocator
-//   warps 4-7 : epilogue, TMEM -> registers -> affine/ReLU -> fp16 -> global; double-buffered accumulators
-//               so the epilogue of tile i overlaps the main loop of tile i+1.
+// Warp roles (320 threads, 1 CTA / SM, persistent over tiles; CTA pairs: see ConvCfg::PAIR):
+//   warp 0 : TMA producer (one elected lane)      smem ring of STAGES x {A block(s), weight tile(s)} -- a plain stage is one tap x one
+//            64-channel slice, a halo stage the (th+2)-row A block of one column offset + the weight tiles of its 2-3 taps
+//   warp 1 : tcgen05.mma issuer (one elected lane; in a CTA pair the even CTA issues cta_group::2 MMAs for both)
+//   warps 2-9 : epilogue, TMEM -> registers -> affine/ReLU -> fp16 planes -> global (two warps per TMEM lane quarter, alternate
+//            32-column groups); double-buffered accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
+//            Optional epilogue work: fused 2x2 max-pool (pool_dst), the "dot" contraction with a vector instead of the store
+//            (dot_w / dot_out: attention psi, Final2) and the attention gate on top of it (gate_src)
 #include <cuda.h>
 
 #include <cstdlib>
