@@ -194,6 +194,11 @@ typedef struct nbp_conv_desc {
                                               Attention_block, `x * psi` (nbp_model.py:62), written by the attention GEMM itself in dst_fmt.
                                               gate_src: NHWC tensor [n][h][w][gate_ld] in the sources' format (`precise`), second plane at gate_lo;
                                               32-byte aligned, gate_c % 32 == 0 (64 in mode 2); not with up2x */
+    int dot_n; const float* dot_bias; float* dot_max;   /* dot epilogue with several vectors (0 = 1): dot_w is [dot_n][c_out], dot_n <= 8, and
+                                              dot_out [n][dot_n][h][w] = f(dot_scale * <y, dot_w[o]> + dot_shift + dot_bias[o]) -- a fused
+                                              1x1 convolution to dot_n channels in NCHW fp32 (Final1, nbp_model.py:89,133); dot_bias
+                                              (optional) [dot_n]; dot_max (optional) [n][h][w] = max over o, the heading read-out
+                                              torch.max(predicted_value_map, dim=1) of nbp_planning.py:193 */
 } nbp_conv_desc;
 
 /* tcgen05/TMEM/TMA implicit-GEMM convolution: conv_block / up_conv / Attention_block W_g,W_x (nbp_model.py:8-62) */

@@ -45,7 +45,8 @@ class ConvDesc(C.Structure):
                 ("dst_lo_off", _i), ("out_f32", _i), ("k_chunk", _i), ("dst_fmt", _i), ("pool_fmt", _i), ("w_lo_scale", _f),
                 ("sat_count", _p), ("pool_dst", _p), ("pool_ld", _i), ("pool_lo_off", _i),
                 ("dot_w", _p), ("dot_out", _p), ("dot_scale", _f), ("dot_shift", _f), ("dot_sigmoid", _i),
-                ("gate_src", _p), ("gate_c", _i), ("gate_ld", _i), ("gate_lo", _i)]
+                ("gate_src", _p), ("gate_c", _i), ("gate_ld", _i), ("gate_lo", _i),
+                ("dot_n", _i), ("dot_bias", _p), ("dot_max", _p)]
 
 
 SIGNATURES.update({

@@ -122,6 +122,9 @@ struct ConvKParams {
     // are contracted with dot_w in fp32 and dot_out[pixel] = f(dot * dot_scale + dot_shift), f = sigmoid or identity.  Fuses the 1-channel
     // 1x1 convolution that follows (Attention_block.psi, Final2) so that its input never goes to memory.
     const float* dot_w; float* dot_out; float dot_scale, dot_shift; int dot_sigmoid;
+    int dot_n;                          // 1 .. 8 vectors (rows of dot_w, c_out apart): dot_out is [n][dot_n][oh][ow] (a fused 1x1 conv to dot_n channels)
+    const float* dot_bias;              // optional [dot_n], added after the scale
+    float* dot_max;                     // optional [n][oh][ow]: max over the dot_n outputs (the heading read-out of Final1)
     // optional gate on top of the dot epilogue (Attention_block, nbp_model.py:62): dst[pixel][dst_c_off + c] = gate_src[pixel][c] * f(dot),
     // c < gate_c, written in dst_fmt like a normal output; gate_src is an NHWC tensor in the sources' format (gate_fmt)
     const __half* gate_src; int gate_c, gate_ld, gate_lo, gate_fmt;
@@ -469,7 +472,9 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         const int c_step = dotm ? 1 : EPI_SPLIT;
         const int c_end = (dotm && !gatem && cg0 != 0) ? 0 : BLOCK_N / 32;
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-            float dot = 0.0f;
+            float dot[8];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) dot[o] = 0.0f;
             const int parity = p.up2x ? (tile & 3) : 0;
             const int tpl = p.up2x ? (tile >> 2) : tile;
             int n_tile, mt, tx, ty, tb;
@@ -568,12 +573,17 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                     a[j] = fminf(fmaxf(fmaf(v[j], sc[j], sh[j]), lower), 65504.0f);      // ReLU (lower = 0) and the fp16 range clamp in one
                 }
                 if (dotm) {                          // channels in ascending order, one fused multiply-add each: deterministic
-                    const float4* dw = reinterpret_cast<const float4*>(p.dot_w + n_tile * BLOCK_N + c * 32);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 q = __ldg(dw + j);
-                        dot = fmaf(a[4 * j], q.x, dot); dot = fmaf(a[4 * j + 1], q.y, dot);
-                        dot = fmaf(a[4 * j + 2], q.z, dot); dot = fmaf(a[4 * j + 3], q.w, dot);
+                    for (int o = 0; o < 8; ++o) {
+                        if (o < p.dot_n) {
+                            const float4* dw = reinterpret_cast<const float4*>(p.dot_w + o * (p.n_tiles * BLOCK_N) + n_tile * BLOCK_N + c * 32);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 q = __ldg(dw + j);
+                                dot[o] = fmaf(a[4 * j], q.x, dot[o]); dot[o] = fmaf(a[4 * j + 1], q.y, dot[o]);
+                                dot[o] = fmaf(a[4 * j + 2], q.z, dot[o]); dot[o] = fmaf(a[4 * j + 3], q.w, dot[o]);
+                            }
+                        }
                     }
                     return;
                 }
@@ -627,9 +637,23 @@ conv_gemm_f16(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                 }
                 release();
                 if (dotm) {
-                    float z = fmaf(dot, p.dot_scale, p.dot_shift);
-                    if (p.dot_sigmoid) z = 1.0f / (1.0f + expf(-z));
-                    if (p.dot_out && cg0 == 0 && valid) p.dot_out[opix] = z;
+                    float zs[8];
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        zs[o] = fmaf(dot[o], p.dot_scale, p.dot_shift + ((p.dot_bias && o < p.dot_n) ? __ldg(p.dot_bias + o) : 0.0f));
+                        if (p.dot_sigmoid) zs[o] = 1.0f / (1.0f + expf(-zs[o]));
+                    }
+                    const float z = zs[0];
+                    if (p.dot_out && cg0 == 0 && valid) {
+                        // NCHW fp32 [n][dot_n][oh][ow] (dot_n = 1: one value per pixel)
+                        const size_t ohw = (size_t)oh * ow, pin = (size_t)oy * ow + ox;
+                        float vmax = -INFINITY;
+#pragma unroll
+                        for (int o = 0; o < 8; ++o) {
+                            if (o < p.dot_n) { p.dot_out[((size_t)nn * p.dot_n + o) * ohw + pin] = zs[o]; vmax = fmaxf(vmax, zs[o]); }
+                        }
+                        if (p.dot_max) p.dot_max[(size_t)nn * ohw + pin] = vmax;
+                    }
                     if (gatem && valid) {
                         // this pixel's gate_c channels times z, 32 channels at a time, alternate groups per warp of the lane quarter
                         const __half* xp = p.gate_src + opix * p.gate_ld;
@@ -829,6 +853,9 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     if (!d->src0 || !d->weight || !d->scale || !d->shift || (!d->dst && !dotm)) return invalid("nbp_conv_fwd: null pointer in descriptor");
     if (dot_any && (!d->dot_w || d->out_f32 || d->pool_dst || (d->c_out != 32 && d->c_out != 64 && d->c_out != 128) || ((uintptr_t)d->dot_w & 15)))
         return invalid("nbp_conv_fwd: the dot epilogue needs dot_w (16-byte aligned), c_out = 32, 64 or 128 (one n-tile; got %d), no fp32 / pooled output", d->c_out);
+    const int dot_n = d->dot_n > 0 ? d->dot_n : 1;
+    if (dot_any && (dot_n > 8 || (gate && dot_n != 1) || (d->dot_max && !d->dot_out)))
+        return invalid("nbp_conv_fwd: dot_n must be 1..8 (1 with a gate); dot_max needs dot_out (dot_n=%d)", d->dot_n);
     if (gate) {
         const int gfmt = d->precise;                                          // the gate source is in the sources' format
         if (d->up2x || d->gate_c <= 0 || d->gate_c % 32 || d->gate_ld % 16 || ((uintptr_t)d->gate_src & 31) ||
@@ -942,6 +969,7 @@ extern "C" int nbp_conv_fwd(const nbp_conv_desc* d, void* stream) {
     kp.dst = (__half*)d->dst; kp.dst_ld = d->dst_ld; kp.dst_c_off = d->dst_c_off; kp.dst_lo_off = d->dst_lo_off;
     kp.pool = (__half*)d->pool_dst; kp.pool_ld = d->pool_ld; kp.pool_lo_off = d->pool_lo_off;
     kp.dot_w = dot_any ? d->dot_w : nullptr; kp.dot_out = d->dot_out; kp.dot_scale = d->dot_scale; kp.dot_shift = d->dot_shift; kp.dot_sigmoid = d->dot_sigmoid ? 1 : 0;
+    kp.dot_n = dot_n; kp.dot_bias = dot_any ? d->dot_bias : nullptr; kp.dot_max = dot_any ? d->dot_max : nullptr;
     kp.gate_src = (const __half*)d->gate_src; kp.gate_c = d->gate_c; kp.gate_ld = d->gate_ld; kp.gate_lo = d->gate_lo; kp.gate_fmt = d->precise;
     if (d->pool_dst) {
         if (d->up2x || d->out_f32) return invalid("nbp_conv_fwd: pool_dst cannot be combined with up2x / out_f32");

@@ -175,6 +175,10 @@ FUSE_DOT = os.environ.get("NBP_FUSE_DOT", "1") != "0"
 # it is a wash (8.71-8.81 ms per 32-scene forward without, 8.68-8.90 with) -- the thread-per-pixel epilogue reads and writes the skip
 # tensor in 32-byte pieces, which costs what the coalesced streaming kernel it replaces cost
 FUSE_GATE = os.environ.get("NBP_FUSE_GATE", "0") != "0"
+# Final1 (8 headings + their max) in the dot epilogue of Up_conv4_1.b (nbp_conv_desc.dot_n = 8).  Built, tested, and OFF: measured a wash
+# (9.05-9.08 ms per 32-scene forward with the separate 75 us head kernel, 9.10-9.12 ms fused: 8 x 128 FMAs and 256 weight loads per pixel
+# in a thread-per-pixel epilogue cost what the streaming head kernel costs)
+FUSE_HEAD8 = os.environ.get("NBP_FUSE_HEAD8", "0") != "0"
 
 
 def _pack_gemm_weight(w2d, precise):
@@ -317,8 +321,9 @@ class _Act:
 
 
 def _conv(pk, layer, B, src0, taps, dst, relu=True, src1=None, up2x=False, k_chunk=0, pool=None, dot=None, gate=None):
-    """``dot`` = (w [c_out] fp32, scale, shift, sigmoid, out fp32 [B,h,w] or None): the dot epilogue of nbp_conv_desc -- the layer's output
-    is contracted with ``w`` per pixel instead of being stored (``dst`` is None then).  ``gate`` (an _Act in the sources' format, with
+    """``dot`` = (w [c_out] fp32, scale, shift, sigmoid, out fp32 [B,h,w] or None[, n, bias [n] or None, max [B,h,w] or None]): the dot
+    epilogue of nbp_conv_desc -- the layer's output is contracted with ``w`` per pixel instead of being stored (``dst`` is None then);
+    with ``n`` > 1, ``w`` is [n][c_out] and ``out`` [B,n,h,w] (a fused 1x1 convolution to n channels, plus its max over the channels).  ``gate`` (an _Act in the sources' format, with
     ``dot``): ``dst`` receives gate * f(dot) instead (Attention_block's x * psi)."""
     mode = layer.get("mode", 1 if pk["precise"] else 0)
     if mode and (src0.fmt != mode or (src1 is not None and src1.fmt != mode)):
@@ -335,7 +340,10 @@ def _conv(pk, layer, B, src0, taps, dst, relu=True, src1=None, up2x=False, k_chu
                       dot[0].data_ptr() if dot is not None else None, dot[4].data_ptr() if dot is not None and dot[4] is not None else None,
                       dot[1] if dot is not None else 0.0, dot[2] if dot is not None else 0.0, (1 if dot[3] else 0) if dot is not None else 0,
                       gate.ptr if gate is not None else None, gate.c if gate is not None else 0, gate.ld if gate is not None else 0,
-                      gate.lo if gate is not None else 0)
+                      gate.lo if gate is not None else 0,
+                      dot[5] if dot is not None and len(dot) > 5 else 0,
+                      dot[6].data_ptr() if dot is not None and len(dot) > 6 and dot[6] is not None else None,
+                      dot[7].data_ptr() if dot is not None and len(dot) > 7 and dot[7] is not None else None)
     _lib.check(_lib.lib().nbp_conv_fwd(ctypes.byref(d), _stream()), "nbp_conv_fwd")
 
 
@@ -467,8 +475,13 @@ def _forward_eval(pk, x, out1, out2, vmax):
     assert out1.is_contiguous() and out2.is_contiguous() and vmax.is_contiguous()
     # ---- decoder 1 -> value map at S/4 (+ its max over the 8 headings)
     d = decoder_stage(skips[5], 5, 1, mode("Up4_1"))
-    d = decoder_stage(d, 4, 1, 1)                         # read by the CUDA-core head only: keep the 22-bit format
-    head("Final1", d, False, out1, vmax)
+    f1 = pk["Final1"]
+    if FUSE_HEAD8 and FUSE_DOT and f1["w"].shape[0] <= 8 and f1["w"].shape[1] in (32, 64, 128):
+        # Final1 (1x1 conv to the 8 headings, nbp_model.py:89,133) and its max over the headings inside the epilogue of Up_conv4_1's second conv
+        decoder_stage(d, 4, 1, 1, dot=(f1["w"].reshape(-1), 1.0, 0.0, False, out1, f1["w"].shape[0], f1["b"], vmax))
+    else:
+        d = decoder_stage(d, 4, 1, 1)                     # read by the CUDA-core head only: keep the 22-bit format
+        head("Final1", d, False, out1, vmax)
     # ---- decoder 2 -> obstacle map at S
     d = decoder_stage(skips[5], 5, 2, mode("Up4_2"))
     for lvl in (4, 3):

@@ -457,6 +457,19 @@ def test_conv_dot_epilogue_equals_conv_then_1x1(n, h, w, c0, c1, cout, taps, up,
         bound = 3e-6 * ((act.abs() * wv.double().abs()).sum(-1) * 1.7 + 1.0)    # fp32 dot of un-rounded activations vs the 22-bit stored ones
         err = (out.cpu().double() - ref).abs()
         assert (err <= bound).all(), f"max err {err.max().item():.3e}"
+        if cout == 128 and not sig:
+            # eight vectors at once (Final1: 1x1 conv to the 8 headings + bias, NCHW output, and the max over the headings)
+            w8 = torch.randn(8, cout, generator=g) / cout ** 0.5
+            b8 = torch.randn(8, generator=g)
+            out8 = torch.full((n, 8, oh, ow), 7.0, dtype=torch.float32, device=DEV)
+            max8 = torch.full((n, oh, ow), 7.0, dtype=torch.float32, device=DEV)
+            M._conv({"precise": True}, layer, n, a0, taps, None, relu=True, src1=a1, up2x=bool(up),
+                    dot=(w8.to(DEV).reshape(-1), 1.0, 0.0, False, out8, 8, b8.to(DEV), max8))
+            torch.cuda.synchronize()
+            ref8 = torch.einsum("nhwc,oc->nohw", act, w8.double()) + b8.double()[None, :, None, None]
+            bound8 = 3e-6 * (torch.einsum("nhwc,oc->nohw", act.abs(), w8.double().abs()) + 1.0)
+            assert ((out8.cpu().double() - ref8).abs() <= bound8).all()
+            assert torch.equal(max8, out8.amax(dim=1))
         if up:
             continue
         # gate on top (Attention_block's x * psi): dst[:, 32 : 32 + gc] = gate * f(dot), written in both output formats inside a wider
